@@ -1,0 +1,789 @@
+// gem_api.cu -- host side of libgem_b200.so: the extern "C" ABI of include/gem_b200.h.
+//
+// Replaces the host wrappers of the reference's gpu_process.cu (Init_GPU_elevationmap :940,
+// Move :1004, Process_points :1085, Mapvar_update :1146, Fuse :1154, Map_optmove :1215,
+// Map_closeloop :1235, Map_feature :1256, Raytracing :1304).  Differences by design:
+// per-handle state instead of __device__ globals, one stream per handle, zero per-call
+// cudaMalloc/cudaFree (the reference does 8+7+9 per frame), geometry passed as kernel
+// parameters instead of cudaMemcpyTo/FromSymbol round trips, int status codes.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gem_b200.h"
+#include "gem_kernels.cuh"
+#include "gem_route.cuh"
+
+using namespace gem;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Region {
+    int kind; // 0 = all cells, 1 = rows [start, start+n), 2 = cols [start, start+n)
+    int start, n;
+};
+
+} // namespace
+
+struct gem_map {
+    gem_config cfg{};
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int L = 0;
+    size_t nc = 0; // cells held by this handle
+    int P = 0;     // per-launch point capacity
+    MapGeom geom{};
+    MapLayers ml{};
+    Scratch sc{};
+    float sensorZ = 0.0f;
+    std::vector<Region> pending; // regions whose variance still needs the gpu.cu:533 floor
+    // staging (device), lazily allocated
+    void *d_xyzi = nullptr, *d_rgba = nullptr, *d_pcl = nullptr;
+    float *d_x = nullptr, *d_y = nullptr, *d_z = nullptr, *d_xt = nullptr, *d_yt = nullptr;
+    int *d_keyin = nullptr, *d_R = nullptr, *d_G = nullptr, *d_B = nullptr;
+    float *d_int = nullptr;
+    float *d_out = nullptr; // 9 * nc floats read-out staging
+    int *d_owner_cnt = nullptr;
+    Counters *h_ctr = nullptr; // pinned
+    gem_stats stats{};
+    std::string err;
+    std::vector<void *> allocs;
+};
+
+namespace {
+
+int fail(gem_map *m, int code, const std::string &msg)
+{
+    if (m) m->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define GEM_CUDA(m, expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            return fail((m), GEM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+        }                                                                                      \
+    } while (0)
+
+template <typename T> int dev_alloc(gem_map *m, T **p, size_t count)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) return fail(m, GEM_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    m->allocs.push_back(q);
+    *p = (T *)q;
+    return GEM_OK;
+}
+
+inline int blocks_for(size_t n, int bs, int cap = 148 * 16)
+{
+    size_t b = (n + bs - 1) / bs;
+    if (b < 1) b = 1;
+    if ((size_t)cap < b) b = cap;
+    return (int)b;
+}
+
+struct SetDev {
+    int prev = -1;
+    explicit SetDev(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); else prev = -1; }
+    ~SetDev() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+FrameParams make_frame(const gem_frame *f)
+{
+    FrameParams p;
+    memset(&p, 0, sizeof p);
+    for (int i = 0; i < 12; i++) p.T[i] = f->T[i];
+    for (int i = 0; i < 3; i++) { p.sJ[i] = f->sensor_jacobian[i]; p.P[i] = f->P_mul_C_BM_transpose[i]; }
+    p.has_rot = 0;
+    for (int i = 0; i < 9; i++) {
+        p.rotVar[i] = f->rotation_variance[i];
+        p.CSBT[i] = f->C_SB_transpose[i];
+        p.Bskew[i] = f->B_r_BS_skew[i];
+        if (f->rotation_variance[i] != 0.0f) p.has_rot = 1;
+    }
+    p.lo = f->rel_lower;
+    p.hi = f->rel_upper;
+    p.sensor_type = f->sensor.type;
+    p.min_r = f->sensor.min_radius;
+    p.beam_a = f->sensor.beam_angle;
+    p.beam_c = f->sensor.beam_constant;
+    p.nf_a = f->sensor.normal_factor_a;
+    p.nf_b = f->sensor.normal_factor_b;
+    p.nf_c = f->sensor.normal_factor_c;
+    p.nf_d = f->sensor.normal_factor_d;
+    p.nf_e = f->sensor.normal_factor_e;
+    p.lat = f->sensor.lateral_factor;
+    return p;
+}
+
+// apply the pending every-cell variance floor (gpu.cu:533-534) where it can matter
+int flush_pending_floor(gem_map *m)
+{
+    for (const Region &r : m->pending) {
+        if (r.kind == 0) {
+            k_floor_range<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, 0, m->nc);
+        } else if (r.kind == 1) {
+            const size_t cnt = (size_t)r.n * m->L;
+            k_floor_range<<<blocks_for(cnt, 256), 256, 0, m->stream>>>(m->ml, (size_t)r.start * m->L, cnt);
+        } else {
+            k_floor_cols<<<blocks_for((size_t)r.n * m->L, 256), 256, 0, m->stream>>>(m->ml, m->L, r.start, r.n);
+        }
+    }
+    m->pending.clear();
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
+// K2..K4 after the binning kernel of the current chunk
+template <int ATTR>
+int run_group_fold(gem_map *m, const AttrInput &a, int n, bool do_fuse, bool do_lowest)
+{
+    k_alloc_cells<<<blocks_for((size_t)n, 256, 148 * 4), 256, 0, m->stream>>>(m->sc);
+    k_scatter<ATTR><<<blocks_for((size_t)n, 256, 1 << 30), 256, 0, m->stream>>>(a, n, m->sc);
+    const int fb = blocks_for((size_t)n, FOLD_WARPS, 148 * 9);
+    k_fold<<<fb, FOLD_WARPS * 32, 0, m->stream>>>(m->geom, m->ml, m->sc, do_fuse ? 1 : 0, do_lowest ? 1 : 0);
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
+int read_counters(gem_map *m, long long n_in, bool accumulate)
+{
+    GEM_CUDA(m, cudaMemcpyAsync(m->h_ctr, m->sc.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    if (!accumulate) memset(&m->stats, 0, sizeof m->stats);
+    m->stats.points_in += n_in;
+    m->stats.points_binned += m->h_ctr->total;
+    m->stats.cells_touched += m->h_ctr->ntouched;
+    int mk = m->h_ctr->maxk;
+    if (mk < 1 && m->h_ctr->ntouched > 0) mk = 1;
+    if (mk > m->stats.max_points_per_cell) m->stats.max_points_per_cell = mk;
+    return GEM_OK;
+}
+
+int ensure_host_staging(gem_map *m)
+{
+    if (m->d_xyzi) return GEM_OK;
+    int rc;
+    if ((rc = dev_alloc(m, (float4 **)&m->d_xyzi, (size_t)m->P))) return rc;
+    if ((rc = dev_alloc(m, (uchar4 **)&m->d_rgba, (size_t)m->P))) return rc;
+    return GEM_OK;
+}
+int ensure_pcl_staging(gem_map *m)
+{
+    if (m->d_pcl) return GEM_OK;
+    return dev_alloc(m, (float4 **)&m->d_pcl, (size_t)m->P * 2);
+}
+int ensure_compat_staging(gem_map *m)
+{
+    if (m->d_x) return GEM_OK;
+    int rc;
+    const size_t P = (size_t)m->P;
+    if ((rc = dev_alloc(m, &m->d_x, P))) return rc;
+    if ((rc = dev_alloc(m, &m->d_y, P))) return rc;
+    if ((rc = dev_alloc(m, &m->d_z, P))) return rc;
+    if ((rc = dev_alloc(m, &m->d_xt, P))) return rc;
+    if ((rc = dev_alloc(m, &m->d_yt, P))) return rc;
+    if ((rc = dev_alloc(m, &m->d_keyin, P))) return rc;
+    if ((rc = dev_alloc(m, &m->d_R, P))) return rc;
+    if ((rc = dev_alloc(m, &m->d_G, P))) return rc;
+    if ((rc = dev_alloc(m, &m->d_B, P))) return rc;
+    if ((rc = dev_alloc(m, &m->d_int, P))) return rc;
+    return GEM_OK;
+}
+int ensure_out_staging(gem_map *m)
+{
+    if (m->d_out) return GEM_OK;
+    return dev_alloc(m, &m->d_out, m->nc * 9);
+}
+
+// one chunk of the fused path on device-resident input
+template <int IN, int ATTR>
+int add_chunk(gem_map *m, const PointInput &in, const AttrInput &a, int n, const FrameParams &fp)
+{
+    GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
+    k_transform_bin<IN><<<blocks_for((size_t)n, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, fp, in, n, m->sc,
+                                                                                 nullptr, nullptr, nullptr);
+    return run_group_fold<ATTR>(m, a, n, true, true);
+}
+
+} // namespace
+
+// =========================================================================================
+extern "C" {
+
+int gem_version(void) { return GEM_B200_VERSION; }
+
+const char *gem_last_error(const gem_map *m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+int gem_create(const gem_config *cfg, gem_map **out)
+{
+    if (!cfg || !out) return fail(nullptr, GEM_ERR_INVALID, "gem_create: null argument");
+    *out = nullptr;
+    if (cfg->length < 1 || cfg->length > 46340 || !(cfg->resolution > 0.0f))
+        return fail(nullptr, GEM_ERR_INVALID, "gem_create: length must be in [1,46340] and resolution > 0");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1)
+        return fail(nullptr, GEM_ERR_NO_DEVICE,
+                    std::string("gem_create: no CUDA device (libgem_b200 has no CPU fallback): ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    int dev = cfg->device;
+    if (dev < 0) {
+        e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return fail(nullptr, GEM_ERR_NO_DEVICE, cudaGetErrorString(e));
+    }
+    if (dev >= ndev) return fail(nullptr, GEM_ERR_INVALID, "gem_create: device ordinal out of range");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return fail(nullptr, GEM_ERR_NO_DEVICE, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, GEM_ERR_NO_DEVICE,
+                    "gem_create: this library carries sm_100a code only (found compute capability " +
+                        std::to_string(prop.major) + "." + std::to_string(prop.minor) + ")");
+
+    gem_map *m = new gem_map();
+    m->cfg = *cfg;
+    m->dev = dev;
+    SetDev sd(dev);
+    m->L = cfg->length;
+    const bool tiled = cfg->tile_rows > 0 && cfg->tile_cols > 0;
+    if (tiled) {
+        if (cfg->tile_row0 < 0 || cfg->tile_col0 < 0 || cfg->tile_row0 + cfg->tile_rows > m->L ||
+            cfg->tile_col0 + cfg->tile_cols > m->L) {
+            delete m;
+            return fail(nullptr, GEM_ERR_INVALID, "gem_create: tile outside the map");
+        }
+    }
+    m->geom.L = m->L;
+    m->geom.res = cfg->resolution;
+    m->geom.cx = m->geom.cy = 0.0f; // gpu.cu:942
+    m->geom.sx = m->geom.sy = 0;    // gpu.cu:943
+    m->geom.box_filter = cfg->compat_box_filter ? 1 : 0;
+    m->geom.tiled = tiled ? 1 : 0;
+    m->geom.r0 = tiled ? cfg->tile_row0 : 0;
+    m->geom.rows = tiled ? cfg->tile_rows : m->L;
+    m->geom.c0 = tiled ? cfg->tile_col0 : 0;
+    m->geom.cols = tiled ? cfg->tile_cols : m->L;
+    m->nc = (size_t)m->geom.rows * m->geom.cols;
+    m->P = cfg->max_points > 0 ? cfg->max_points : (1 << 21);
+
+    int rc = GEM_OK;
+    auto bail = [&](int code) {
+        std::string msg = m->err;
+        gem_destroy(m);
+        g_create_error = msg;
+        return code;
+    };
+    if (cfg->stream) {
+        m->stream = (cudaStream_t)cfg->stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { m->err = cudaGetErrorString(e); return bail(GEM_ERR_CUDA); }
+        m->own_stream = true;
+    }
+    const size_t nc = m->nc, P = (size_t)m->P;
+    if ((rc = dev_alloc(m, &m->ml.ev, nc)) || (rc = dev_alloc(m, &m->ml.ci, nc)) ||
+        (rc = dev_alloc(m, &m->ml.traver, nc)) || (rc = dev_alloc(m, &m->ml.lowest, nc)) ||
+        (rc = dev_alloc(m, &m->ml.rough, nc)) || (rc = dev_alloc(m, &m->ml.slope, nc)) ||
+        (rc = dev_alloc(m, &m->ml.traver_out, nc)) || (rc = dev_alloc(m, &m->sc.cnt, nc)) ||
+        (rc = dev_alloc(m, &m->sc.cellBase, nc)) || (rc = dev_alloc(m, &m->sc.touched, P < nc ? P : nc)) ||
+        (rc = dev_alloc(m, &m->sc.ctr, 1)) || (rc = dev_alloc(m, &m->sc.key, P)) ||
+        (rc = dev_alloc(m, &m->sc.rank, P)) || (rc = dev_alloc(m, &m->sc.h, P)) ||
+        (rc = dev_alloc(m, &m->sc.hv, P)) || (rc = dev_alloc(m, &m->sc.recA, P)) ||
+        (rc = dev_alloc(m, &m->sc.recI, P)))
+        return bail(rc);
+    e = cudaHostAlloc((void **)&m->h_ctr, sizeof(Counters), cudaHostAllocDefault);
+    if (e != cudaSuccess) { m->err = cudaGetErrorString(e); return bail(GEM_ERR_CUDA); }
+    // G_Init_map gpu.cu:198-214
+    k_clear_range<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml, 0, nc, 2);
+    k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.rough, nc, 0.0f);
+    k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.slope, nc, 0.0f);
+    k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.traver_out, nc, -10.0f);
+    e = cudaMemsetAsync(m->sc.cnt, 0, nc * sizeof(int), m->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) {
+        m->err = std::string("gem_create: init kernels failed (is the device sm_100?): ") + cudaGetErrorString(e);
+        return bail(GEM_ERR_NO_DEVICE);
+    }
+    m->pending.push_back(Region{0, 0, 0}); // first Fuse floors every cell
+    *out = m;
+    return GEM_OK;
+}
+
+int gem_destroy(gem_map *m)
+{
+    if (!m) return GEM_OK;
+    SetDev sd(m->dev);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (void *p : m->allocs) cudaFree(p);
+    if (m->h_ctr) cudaFreeHost(m->h_ctr);
+    if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return GEM_OK;
+}
+
+int gem_sync(gem_map *m)
+{
+    if (!m) return GEM_ERR_INVALID;
+    SetDev sd(m->dev);
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return GEM_OK;
+}
+
+// ---- Move gpu.cu:1004-1083 -----------------------------------------------------------------
+static int index_to_range(int index, int L)
+{ // gpu.cu:916-921
+    if (index < 0) index += ((-index / L) + 1) * L;
+    return index % L;
+}
+static int d2i_host(double d)
+{ // cvt.rzi semantics for the host-side casts of gpu.cu:897,998-999
+    if (d != d) return 0;
+    if (d >= 2147483648.0) return 2147483647;
+    if (d <= -2147483649.0) return -2147483647 - 1;
+    return (int)d;
+}
+static float position_to_range(float p, float shift, float resolution)
+{ // gpu.cu:996-1002
+    const int p_index = d2i_host((double)roundf(p / resolution));
+    const int shift_index = d2i_host((double)roundf(shift / resolution));
+    return (float)(p_index + shift_index) * resolution;
+}
+static void clear_rows(gem_map *m, int start, int n)
+{
+    const size_t cnt = (size_t)n * m->L;
+    k_clear_range<<<blocks_for(cnt, 256), 256, 0, m->stream>>>(m->ml, (size_t)start * m->L, cnt, 0);
+    m->pending.push_back(Region{1, start, n});
+}
+static void clear_cols(gem_map *m, int start, int n)
+{
+    k_clear_cols<<<blocks_for((size_t)n * m->L, 256), 256, 0, m->stream>>>(m->ml, m->L, start, n);
+    m->pending.push_back(Region{2, start, n});
+}
+
+int gem_move(gem_map *m, const float pos[3], float centre_out[2], int start_out[2], float shift_out[2])
+{
+    if (!m || !pos) return fail(m, GEM_ERR_INVALID, "gem_move: null argument");
+    SetDev sd(m->dev);
+    const int L = m->L;
+    m->sensorZ = pos[2]; // gpu.cu:1011-1012
+    float aligned[2] = {0.0f, 0.0f};
+    if (m->geom.tiled) {
+        // tiled (multi-GPU) maps are global, non-scrolling maps
+        if (centre_out) { centre_out[0] = m->geom.cx; centre_out[1] = m->geom.cy; }
+        if (start_out) { start_out[0] = 0; start_out[1] = 0; }
+        if (shift_out) { shift_out[0] = 0.0f; shift_out[1] = 0.0f; }
+        return GEM_OK;
+    }
+    float centre[2] = {m->geom.cx, m->geom.cy};
+    int start[2] = {m->geom.sx, m->geom.sy};
+    int indexShift[2];
+    for (int i = 0; i < 2; i++) {
+        const float ps = pos[i] - centre[i];
+        indexShift[i] = d2i_host((double)(ps / m->geom.res) + 0.5 * (ps > 0 ? 1 : -1)); // gpu.cu:897
+        aligned[i] = (float)indexShift[i] * m->geom.res;                                   // gpu.cu:909
+    }
+    for (int i = 0; i < 2; i++) {
+        if (indexShift[i] != 0) {
+            // |shift| >= L clears everything (the reference tests only the positive side,
+            // gpu.cu:1033, and would write out of bounds for shift <= -L)
+            if (indexShift[i] >= L || indexShift[i] <= -L) {
+                k_clear_range<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, 0, m->nc, 1);
+                m->pending.clear();
+                m->pending.push_back(Region{0, 0, 0});
+            } else {
+                const int sign = indexShift[i] > 0 ? 1 : -1;
+                const int startIndex = start[i] - (sign > 0 ? 1 : 0);
+                const int endIndex = startIndex + sign - indexShift[i];
+                const int nCells = std::abs(indexShift[i]);
+                int index = sign < 0 ? startIndex : endIndex;
+                index = index_to_range(index, L);
+                if (index + nCells <= L) {
+                    if (i == 0) clear_rows(m, index, nCells); else clear_cols(m, index, nCells);
+                } else {
+                    const int firstn = L - index, secondn = nCells - firstn;
+                    if (i == 0) { clear_rows(m, index, firstn); clear_rows(m, 0, secondn); }
+                    else { clear_cols(m, index, firstn); clear_cols(m, 0, secondn); }
+                }
+            }
+        }
+        start[i] = index_to_range(start[i] - indexShift[i], L);
+        centre[i] = position_to_range(centre[i], aligned[i], m->geom.res);
+    }
+    m->geom.cx = centre[0]; m->geom.cy = centre[1];
+    m->geom.sx = start[0]; m->geom.sy = start[1];
+    if (centre_out) { centre_out[0] = centre[0]; centre_out[1] = centre[1]; }
+    if (start_out) { start_out[0] = start[0]; start_out[1] = start[1]; }
+    if (shift_out) { shift_out[0] = aligned[0]; shift_out[1] = aligned[1]; }
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
+// ---- fused add -------------------------------------------------------------------------------
+int gem_add_points(gem_map *m, const void *xyzi, const void *rgba, int n, const gem_frame *frame)
+{
+    if (!m || !frame || n < 0 || (n > 0 && !xyzi)) return fail(m, GEM_ERR_INVALID, "gem_add_points: bad argument");
+    SetDev sd(m->dev);
+    int rc = flush_pending_floor(m);
+    if (rc) return rc;
+    const FrameParams fp = make_frame(frame);
+    memset(&m->stats, 0, sizeof m->stats);
+    for (int off = 0; off < n; off += m->P) {
+        const int cn = (n - off < m->P) ? (n - off) : m->P;
+        PointInput in{};
+        in.xyzi = (const float4 *)xyzi + off;
+        in.rgba = rgba ? (const uchar4 *)rgba + off : nullptr;
+        AttrInput a{};
+        a.xyzi = in.xyzi;
+        a.rgba = in.rgba;
+        if ((rc = add_chunk<IN_XYZI, ATTR_XYZI>(m, in, a, cn, fp))) return rc;
+        if (n > m->P && (rc = read_counters(m, cn, true))) return rc; // chunked: keep totals
+    }
+    if (n <= m->P) m->stats.points_in = n; // counters are fetched lazily by gem_get_stats
+    return GEM_OK;
+}
+
+int gem_add_points_host(gem_map *m, const void *xyzi, const void *rgba, int n, const gem_frame *frame)
+{
+    if (!m || !frame || n < 0 || (n > 0 && !xyzi)) return fail(m, GEM_ERR_INVALID, "gem_add_points_host: bad argument");
+    SetDev sd(m->dev);
+    int rc = ensure_host_staging(m);
+    if (rc) return rc;
+    if ((rc = flush_pending_floor(m))) return rc;
+    const FrameParams fp = make_frame(frame);
+    memset(&m->stats, 0, sizeof m->stats);
+    for (int off = 0; off < n || (n == 0 && off == 0); off += m->P) {
+        const int cn = (n - off < m->P) ? (n - off) : m->P;
+        if (cn > 0) {
+            GEM_CUDA(m, cudaMemcpyAsync(m->d_xyzi, (const float4 *)xyzi + off, (size_t)cn * 16, cudaMemcpyHostToDevice, m->stream));
+            if (rgba)
+                GEM_CUDA(m, cudaMemcpyAsync(m->d_rgba, (const uchar4 *)rgba + off, (size_t)cn * 4, cudaMemcpyHostToDevice, m->stream));
+        }
+        PointInput in{};
+        in.xyzi = (const float4 *)m->d_xyzi;
+        in.rgba = rgba ? (const uchar4 *)m->d_rgba : nullptr;
+        AttrInput a{};
+        a.xyzi = in.xyzi;
+        a.rgba = in.rgba;
+        if ((rc = add_chunk<IN_XYZI, ATTR_XYZI>(m, in, a, cn, fp))) return rc;
+        if ((rc = read_counters(m, cn, true))) return rc; // also the host-visible completion point
+        if (n == 0) break;
+    }
+    return GEM_OK;
+}
+
+int gem_add_cloud_pcl_host(gem_map *m, const void *pts, int n, const gem_frame *frame)
+{
+    if (!m || !frame || n < 0 || (n > 0 && !pts)) return fail(m, GEM_ERR_INVALID, "gem_add_cloud_pcl_host: bad argument");
+    SetDev sd(m->dev);
+    int rc = ensure_pcl_staging(m);
+    if (rc) return rc;
+    if ((rc = flush_pending_floor(m))) return rc;
+    const FrameParams fp = make_frame(frame);
+    memset(&m->stats, 0, sizeof m->stats);
+    for (int off = 0; off < n || (n == 0 && off == 0); off += m->P) {
+        const int cn = (n - off < m->P) ? (n - off) : m->P;
+        if (cn > 0)
+            GEM_CUDA(m, cudaMemcpyAsync(m->d_pcl, (const char *)pts + (size_t)off * 32, (size_t)cn * 32, cudaMemcpyHostToDevice, m->stream));
+        PointInput in{};
+        in.pcl = (const float4 *)m->d_pcl;
+        AttrInput a{};
+        a.pcl = in.pcl;
+        if ((rc = add_chunk<IN_PCL32, ATTR_PCL32>(m, in, a, cn, fp))) return rc;
+        if ((rc = read_counters(m, cn, true))) return rc;
+        if (n == 0) break;
+    }
+    return GEM_OK;
+}
+
+// ---- unfused reference calls ---------------------------------------------------------------
+int gem_process_points(gem_map *m, int *map_index, const float *x, const float *y, const float *z, float *var,
+                       float *x_ts, float *y_ts, float *z_ts, int n, const gem_frame *frame)
+{
+    if (!m || !frame || n < 0 || (n > 0 && (!x || !y || !z)))
+        return fail(m, GEM_ERR_INVALID, "gem_process_points: bad argument");
+    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_process_points: not available on tiled handles");
+    SetDev sd(m->dev);
+    int rc = ensure_compat_staging(m);
+    if (rc) return rc;
+    const FrameParams fp = make_frame(frame);
+    memset(&m->stats, 0, sizeof m->stats);
+    for (int off = 0; off < n; off += m->P) {
+        const int cn = (n - off < m->P) ? (n - off) : m->P;
+        const size_t b = (size_t)cn * 4;
+        GEM_CUDA(m, cudaMemcpyAsync(m->d_x, x + off, b, cudaMemcpyHostToDevice, m->stream));
+        GEM_CUDA(m, cudaMemcpyAsync(m->d_y, y + off, b, cudaMemcpyHostToDevice, m->stream));
+        GEM_CUDA(m, cudaMemcpyAsync(m->d_z, z + off, b, cudaMemcpyHostToDevice, m->stream));
+        GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
+        PointInput in{};
+        in.x = m->d_x; in.y = m->d_y; in.z = m->d_z;
+        k_transform_bin<IN_SOA><<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(
+            m->geom, fp, in, cn, m->sc, m->d_xt, m->d_yt, nullptr);
+        AttrInput a{};
+        if ((rc = run_group_fold<ATTR_NONE>(m, a, cn, false, true))) return rc; // lowest-scan only
+        if (map_index) GEM_CUDA(m, cudaMemcpyAsync(map_index + off, m->sc.key, b, cudaMemcpyDeviceToHost, m->stream));
+        if (var) GEM_CUDA(m, cudaMemcpyAsync(var + off, m->sc.hv, b, cudaMemcpyDeviceToHost, m->stream));
+        if (z_ts) GEM_CUDA(m, cudaMemcpyAsync(z_ts + off, m->sc.h, b, cudaMemcpyDeviceToHost, m->stream));
+        if (x_ts) GEM_CUDA(m, cudaMemcpyAsync(x_ts + off, m->d_xt, b, cudaMemcpyDeviceToHost, m->stream));
+        if (y_ts) GEM_CUDA(m, cudaMemcpyAsync(y_ts + off, m->d_yt, b, cudaMemcpyDeviceToHost, m->stream));
+        if ((rc = read_counters(m, cn, true))) return rc;
+    }
+    return GEM_OK;
+}
+
+int gem_fuse(gem_map *m, int n, const int *index, const int *R, const int *G, const int *B, const float *intensity,
+             const float *height, const float *var)
+{
+    if (!m || n < 0 || (n > 0 && (!index || !height || !var))) return fail(m, GEM_ERR_INVALID, "gem_fuse: bad argument");
+    SetDev sd(m->dev);
+    int rc = ensure_compat_staging(m);
+    if (rc) return rc;
+    if ((rc = flush_pending_floor(m))) return rc;
+    memset(&m->stats, 0, sizeof m->stats);
+    for (int off = 0; off < n; off += m->P) {
+        const int cn = (n - off < m->P) ? (n - off) : m->P;
+        const size_t b = (size_t)cn * 4;
+        GEM_CUDA(m, cudaMemcpyAsync(m->d_keyin, index + off, b, cudaMemcpyHostToDevice, m->stream));
+        GEM_CUDA(m, cudaMemcpyAsync(m->sc.h, height + off, b, cudaMemcpyHostToDevice, m->stream));
+        GEM_CUDA(m, cudaMemcpyAsync(m->sc.hv, var + off, b, cudaMemcpyHostToDevice, m->stream));
+        AttrInput a{};
+        if (R) { GEM_CUDA(m, cudaMemcpyAsync(m->d_R, R + off, b, cudaMemcpyHostToDevice, m->stream)); a.R = m->d_R; }
+        if (G) { GEM_CUDA(m, cudaMemcpyAsync(m->d_G, G + off, b, cudaMemcpyHostToDevice, m->stream)); a.G = m->d_G; }
+        if (B) { GEM_CUDA(m, cudaMemcpyAsync(m->d_B, B + off, b, cudaMemcpyHostToDevice, m->stream)); a.B = m->d_B; }
+        if (intensity) {
+            GEM_CUDA(m, cudaMemcpyAsync(m->d_int, intensity + off, b, cudaMemcpyHostToDevice, m->stream));
+            a.intensity = m->d_int;
+        }
+        GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
+        k_count_keys<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(m->d_keyin, cn, (int)m->nc, m->sc);
+        if ((rc = run_group_fold<ATTR_INT_ARRAYS>(m, a, cn, true, false))) return rc;
+        if ((rc = read_counters(m, cn, true))) return rc;
+    }
+    return GEM_OK;
+}
+
+int gem_var_update(gem_map *m, float dv)
+{
+    if (!m) return GEM_ERR_INVALID;
+    SetDev sd(m->dev);
+    // x + 0.0f == x for every non-NaN x: the GEM node always passes 0 (ElevationMapping.cpp:944-945)
+    if (dv == 0.0f) return GEM_OK;
+    k_var_update<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, dv);
+    if (dv < 0.0f) { // variances may drop below the floor: next Fuse must floor every cell
+        m->pending.clear();
+        m->pending.push_back(Region{0, 0, 0});
+    }
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
+int gem_compute_features(gem_map *m)
+{
+    if (!m) return GEM_ERR_INVALID;
+    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_compute_features: tiled handles need a halo exchange (not implemented)");
+    SetDev sd(m->dev);
+    k_features<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml);
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
+static int copy_layer_out(gem_map *m, int layer, void *host, int slot)
+{
+    float *dst = m->d_out + (size_t)slot * m->nc;
+    k_unpack_layer<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, layer, dst);
+    GEM_CUDA(m, cudaGetLastError());
+    GEM_CUDA(m, cudaMemcpyAsync(host, dst, m->nc * 4, cudaMemcpyDeviceToHost, m->stream));
+    return GEM_OK;
+}
+
+int gem_map_feature(gem_map *m, float *elevation, float *var, int *R, int *G, int *B, float *rough, float *slope,
+                    float *traver, float *intensity)
+{
+    if (!m) return GEM_ERR_INVALID;
+    int rc = gem_compute_features(m);
+    if (rc) return rc;
+    SetDev sd(m->dev);
+    if ((rc = ensure_out_staging(m))) return rc;
+    struct { void *p; int layer; } outs[9] = {{elevation, 0}, {var, 1}, {R, 3}, {G, 4}, {B, 5},
+                                              {rough, 8}, {slope, 9}, {traver, 10}, {intensity, 2}};
+    for (int k = 0; k < 9; k++)
+        if (outs[k].p && (rc = copy_layer_out(m, outs[k].layer, outs[k].p, k))) return rc;
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return GEM_OK;
+}
+
+int gem_raytracing(gem_map *m)
+{
+    if (!m) return GEM_ERR_INVALID;
+    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_raytracing: tiled handles need replicated lowest (not implemented)");
+    SetDev sd(m->dev);
+    k_raytrace<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, m->sensorZ, m->cfg.obstacle_threshold);
+    k_fill<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml.lowest, m->nc, 10.0f); // G_Clear_maplowest
+    GEM_CUDA(m, cudaGetLastError());
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream)); // gpu.cu:1312
+    return GEM_OK;
+}
+
+int gem_opt_move(gem_map *m, const float opt_p[2], float height_update, float aligned_out[2])
+{
+    if (!m || !opt_p) return GEM_ERR_INVALID;
+    SetDev sd(m->dev);
+    float c[2] = {m->geom.cx, m->geom.cy};
+    for (int i = 0; i < 2; i++) { // alignedPosition gpu.cu:1203-1213
+        const float ps = opt_p[i] - c[i];
+        const int is = d2i_host((double)(ps / m->geom.res) + 0.5 * (ps > 0 ? 1 : -1));
+        c[i] = c[i] + m->geom.res * (float)is;
+        if (aligned_out) aligned_out[i] = c[i];
+    }
+    m->geom.cx = c[0]; m->geom.cy = c[1];
+    k_add_height<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, height_update);
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
+int gem_closeloop(gem_map *m, const float up[2], float height_update)
+{
+    if (!m || !up) return GEM_ERR_INVALID;
+    SetDev sd(m->dev);
+    float c[2] = {m->geom.cx, m->geom.cy};
+    for (int i = 0; i < 2; i++) { // gpu.cu:1242-1247
+        const float ps = up[i] - c[i];
+        const int is = d2i_host((double)(ps / m->geom.res) + 0.5 * (ps > 0 ? 1 : -1));
+        const float aligned = (float)is * m->geom.res;
+        c[i] = position_to_range(c[i], aligned, m->geom.res);
+    }
+    m->geom.cx = c[0]; m->geom.cy = c[1];
+    k_add_height<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, height_update);
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
+int gem_export_layers(gem_map *m, float *host_layers[9])
+{
+    if (!m || !host_layers) return GEM_ERR_INVALID;
+    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_export_layers: not available on tiled handles");
+    SetDev sd(m->dev);
+    int rc = ensure_out_staging(m);
+    if (rc) return rc;
+    dim3 grid((m->L + 31) / 32, (m->L + 31) / 32);
+    k_export_colmajor<<<grid, 256, 0, m->stream>>>(m->ml, m->L, m->d_out);
+    GEM_CUDA(m, cudaGetLastError());
+    for (int k = 0; k < 9; k++)
+        if (host_layers[k])
+            GEM_CUDA(m, cudaMemcpyAsync(host_layers[k], m->d_out + (size_t)k * m->nc, m->nc * 4, cudaMemcpyDeviceToHost, m->stream));
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return GEM_OK;
+}
+
+int gem_get_layer(gem_map *m, int layer, void *host_out)
+{
+    if (!m || !host_out || layer < 0 || layer > 9) return fail(m, GEM_ERR_INVALID, "gem_get_layer: bad argument");
+    SetDev sd(m->dev);
+    int rc = ensure_out_staging(m);
+    if (rc) return rc;
+    if ((rc = copy_layer_out(m, layer, host_out, 0))) return rc;
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return GEM_OK;
+}
+
+int gem_set_layer(gem_map *m, int layer, const void *host_in)
+{
+    if (!m || !host_in || layer < 0 || layer > 9) return fail(m, GEM_ERR_INVALID, "gem_set_layer: bad argument");
+    SetDev sd(m->dev);
+    int rc = ensure_out_staging(m);
+    if (rc) return rc;
+    GEM_CUDA(m, cudaMemcpyAsync(m->d_out, host_in, m->nc * 4, cudaMemcpyHostToDevice, m->stream));
+    k_pack_layer<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, layer, m->d_out);
+    GEM_CUDA(m, cudaGetLastError());
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    if (layer == GEM_LAYER_VARIANCE) {
+        m->pending.clear();
+        m->pending.push_back(Region{0, 0, 0});
+    }
+    return GEM_OK;
+}
+
+int gem_get_state(gem_map *m, float centre[2], int start[2], float *sensor_z)
+{
+    if (!m) return GEM_ERR_INVALID;
+    if (centre) { centre[0] = m->geom.cx; centre[1] = m->geom.cy; }
+    if (start) { start[0] = m->geom.sx; start[1] = m->geom.sy; }
+    if (sensor_z) *sensor_z = m->sensorZ;
+    return GEM_OK;
+}
+
+int gem_get_stats(gem_map *m, gem_stats *out)
+{
+    if (!m || !out) return GEM_ERR_INVALID;
+    SetDev sd(m->dev);
+    if (m->stats.points_in > 0 && m->stats.cells_touched == 0 && m->stats.points_binned == 0) {
+        // device-pointer call: counters not fetched yet
+        const long long n_in = m->stats.points_in;
+        int rc = read_counters(m, 0, false);
+        if (rc) return rc;
+        m->stats.points_in = n_in;
+    }
+    *out = m->stats;
+    return GEM_OK;
+}
+
+int gem_host_alloc(void **out, unsigned long long bytes)
+{
+    if (!out) return GEM_ERR_INVALID;
+    return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? GEM_OK : GEM_ERR_NOMEM;
+}
+int gem_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? GEM_OK : GEM_ERR_CUDA; }
+
+// ---- multi-GPU routing -----------------------------------------------------------------------
+int gem_route_points(gem_map *m, const void *xyzi, const void *rgba, int n, const gem_frame *frame, int tiles_r,
+                     int tiles_c, void *rec_out, int *counts_out)
+{
+    if (!m || !frame || n < 0 || tiles_r < 1 || tiles_c < 1 || !rec_out || !counts_out || (n > 0 && !xyzi))
+        return fail(m, GEM_ERR_INVALID, "gem_route_points: bad argument");
+    if (n > m->P) return fail(m, GEM_ERR_INVALID, "gem_route_points: n exceeds max_points");
+    if (tiles_r * tiles_c > ROUTE_MAX_OWNERS) return fail(m, GEM_ERR_INVALID, "gem_route_points: too many tiles");
+    SetDev sd(m->dev);
+    const FrameParams fp = make_frame(frame);
+    MapGeom gg = m->geom;
+    gg.tiled = 0; // routing works on global geographic indices
+    const cudaError_t e = route_points(m->stream, gg, fp, (const float4 *)xyzi, (const uchar4 *)rgba, n, tiles_r,
+                                       tiles_c, m->sc, m->nc, (RouteRec *)rec_out, counts_out);
+    if (e != cudaSuccess) return fail(m, GEM_ERR_CUDA, std::string("gem_route_points: ") + cudaGetErrorString(e));
+    return GEM_OK;
+}
+
+int gem_fuse_records(gem_map *m, const void *rec, int n)
+{
+    if (!m || n < 0 || (n > 0 && !rec)) return fail(m, GEM_ERR_INVALID, "gem_fuse_records: bad argument");
+    SetDev sd(m->dev);
+    int rc = flush_pending_floor(m);
+    if (rc) return rc;
+    memset(&m->stats, 0, sizeof m->stats);
+    for (int off = 0; off < n; off += m->P) {
+        const int cn = (n - off < m->P) ? (n - off) : m->P;
+        GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
+        k_count_records<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, (const RouteRec *)rec + off, cn, m->sc);
+        k_alloc_cells<<<blocks_for((size_t)cn, 256, 148 * 4), 256, 0, m->stream>>>(m->sc);
+        k_scatter_records<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>((const RouteRec *)rec + off, cn, m->sc);
+        const int fb = blocks_for((size_t)cn, FOLD_WARPS, 148 * 9);
+        k_fold<<<fb, FOLD_WARPS * 32, 0, m->stream>>>(m->geom, m->ml, m->sc, 1, 1);
+        GEM_CUDA(m, cudaGetLastError());
+        if (n > m->P && (rc = read_counters(m, cn, true))) return rc;
+    }
+    if (n <= m->P) m->stats.points_in = n;
+    return GEM_OK;
+}
+
+} // extern "C"

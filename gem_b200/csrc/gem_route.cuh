@@ -1,0 +1,180 @@
+// gem_route.cuh -- point routing for spatially tiled maps (BASELINE configs 4/5).
+//
+// The reference is single-GPU; a map that outgrows one GPU is cut into geographic tiles, one
+// per rank.  Every rank transforms its share of the input, buckets the accepted in-grid
+// points STABLY by owning tile, and the host side exchanges the buckets with one NCCL
+// all-to-all (gem_b200/tiled.py).  Concatenating received buckets in (source rank, source
+// order) reproduces the global point order, so the tiled result is bit-identical to the
+// single-GPU result on the concatenated cloud.
+#pragma once
+#include "gem_kernels.cuh"
+
+namespace gem {
+
+constexpr int ROUTE_MAX_OWNERS = 64;
+constexpr int ROUTE_BLOCK = 256;
+
+struct RouteRec { // 20 bytes on the wire
+    int gkey;     // global geographic linear index gx*L+gy
+    float h, var;
+    uint32_t rgb;
+    float intensity;
+};
+
+// pass 1: transform, owner id, per-block owner histogram
+__global__ void __launch_bounds__(ROUTE_BLOCK)
+k_route_count(MapGeom g, FrameParams f, const float4 *xyzi, int n, int tile_h, int tile_w, int tiles_c,
+              int n_owners, int *owner_out, int *gkey_out, float *h_out, float *hv_out, int *blockCounts /* [owners][blocks] */)
+{
+    __shared__ int s_cnt[ROUTE_MAX_OWNERS];
+    for (int o = threadIdx.x; o < n_owners; o += blockDim.x) s_cnt[o] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int owner = -1;
+    if (i < n) {
+        const float4 p = ld_stream_f4(xyzi + i);
+        const PtRes r = transform_point(g, f, p.x, p.y, p.z);
+        int gkey = -1;
+        if (r.ingrid) {
+            owner = (r.gx / tile_h) * tiles_c + (r.gy / tile_w);
+            gkey = r.gx * g.L + r.gy;
+        }
+        owner_out[i] = owner;
+        gkey_out[i] = gkey;
+        h_out[i] = r.h;
+        hv_out[i] = r.hv;
+    }
+    if (owner >= 0) atomicAdd(&s_cnt[owner], 1);
+    __syncthreads();
+    for (int o = threadIdx.x; o < n_owners; o += blockDim.x) blockCounts[o * gridDim.x + blockIdx.x] = s_cnt[o];
+}
+
+// pass 2: one block scans blockCounts owner-major -> exclusive offsets; owner totals
+__global__ void __launch_bounds__(1024) k_route_scan(int *blockCounts, int n_owners, int nblocks, int *counts_out)
+{
+    __shared__ int s_part[1024];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int total = n_owners * nblocks;
+    int owner_begin_val = 0;
+    for (int base = 0; base < total; base += 1024) {
+        const int idx = base + threadIdx.x;
+        const int v = idx < total ? blockCounts[idx] : 0;
+        s_part[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) { // Hillis-Steele inclusive scan
+            const int t = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0;
+            __syncthreads();
+            s_part[threadIdx.x] += t;
+            __syncthreads();
+        }
+        const int incl = s_part[threadIdx.x] + s_carry;
+        if (idx < total) blockCounts[idx] = incl - v; // exclusive, global over (owner, block)
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    (void)owner_begin_val;
+    // owner totals from consecutive owner starts
+    __syncthreads();
+    for (int o = threadIdx.x; o < n_owners; o += blockDim.x) {
+        const int begin = blockCounts[o * nblocks];
+        const int end = (o + 1 < n_owners) ? blockCounts[(o + 1) * nblocks] : s_carry;
+        counts_out[o] = end - begin;
+    }
+}
+
+// pass 3: stable in-block rank and record write
+__global__ void __launch_bounds__(ROUTE_BLOCK)
+k_route_write(const float4 *xyzi, const uchar4 *rgba, int n, int n_owners, const int *owner_in, const int *gkey_in,
+              const float *h_in, const float *hv_in, const int *blockOffsets, RouteRec *out)
+{
+    __shared__ int s_wcnt[ROUTE_BLOCK / 32][ROUTE_MAX_OWNERS];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const int w = threadIdx.x >> 5;
+    for (int o = (int)lane; o < n_owners; o += 32) s_wcnt[w][o] = 0;
+    __syncwarp();
+    const int owner = (i < n) ? owner_in[i] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, owner);
+    const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (owner >= 0 && rank_in_warp == 0) s_wcnt[w][owner] = __popc(peers);
+    __syncthreads();
+    if (owner >= 0) {
+        int before = 0;
+        for (int ww = 0; ww < w; ww++) before += s_wcnt[ww][owner];
+        const int pos = blockOffsets[owner * gridDim.x + blockIdx.x] + before + rank_in_warp;
+        RouteRec r;
+        r.gkey = gkey_in[i];
+        r.h = h_in[i];
+        r.var = hv_in[i];
+        r.rgb = 0u;
+        if (rgba) {
+            const uchar4 c = rgba[i];
+            r.rgb = pack_rgb(c.x, c.y, c.z);
+        }
+        r.intensity = xyzi[i].w;
+        out[pos] = r;
+    }
+}
+
+// scratch layout for routing reuses the per-point arrays of the handle:
+//   key -> owner, rank -> gkey, h/hv as usual; blockCounts lives in cellBase.
+inline cudaError_t route_points(cudaStream_t st, const MapGeom &g, const FrameParams &fp, const float4 *xyzi,
+                                const uchar4 *rgba, int n, int tiles_r, int tiles_c, const Scratch &sc,
+                                size_t cellBase_capacity, RouteRec *out, int *counts_out)
+{
+    const int n_owners = tiles_r * tiles_c;
+    const int nblocks = n > 0 ? (n + ROUTE_BLOCK - 1) / ROUTE_BLOCK : 1;
+    if ((size_t)n_owners * nblocks > cellBase_capacity) return cudaErrorInvalidValue;
+    const int tile_h = (g.L + tiles_r - 1) / tiles_r, tile_w = (g.L + tiles_c - 1) / tiles_c;
+    k_route_count<<<nblocks, ROUTE_BLOCK, 0, st>>>(g, fp, xyzi, n, tile_h, tile_w, tiles_c, n_owners, sc.key, sc.rank,
+                                                  sc.h, sc.hv, sc.cellBase);
+    k_route_scan<<<1, 1024, 0, st>>>(sc.cellBase, n_owners, nblocks, counts_out);
+    k_route_write<<<nblocks, ROUTE_BLOCK, 0, st>>>(xyzi, rgba, n, n_owners, sc.key, sc.rank, sc.h, sc.hv, sc.cellBase, out);
+    return cudaGetLastError();
+}
+
+// count/scatter for received records (fold happens in k_fold)
+__global__ void __launch_bounds__(256) k_count_records(MapGeom g, const RouteRec *rec, int n, Scratch sc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    int key = -1;
+    bool first = false;
+    if (i < n) {
+        const int gkey = rec[i].gkey;
+        if (gkey >= 0) {
+            const int gx = gkey / g.L, gy = gkey - gx * g.L;
+            key = local_key(g, gx, gy);
+        }
+        sc.key[i] = key;
+        if (key >= 0) {
+            const int rk = atomicAdd(&sc.cnt[key], 1);
+            sc.rank[i] = rk;
+            first = (rk == 0);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, first);
+    if (m) {
+        int base = 0;
+        const int leader = __ffs(m) - 1;
+        if ((int)lane == leader) base = atomicAdd(&sc.ctr->ntouched, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (first) sc.touched[base + __popc(m & ((1u << lane) - 1u))] = key;
+    }
+}
+__global__ void __launch_bounds__(256) k_scatter_records(const RouteRec *rec, int n, Scratch sc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int key = sc.key[i];
+    if (key < 0) return;
+    const int pos = sc.cellBase[key] + sc.rank[i];
+    const RouteRec r = rec[i];
+    sc.recA[pos] = make_uint4((uint32_t)i, __float_as_uint(r.h), __float_as_uint(r.var), r.rgb);
+    sc.recI[pos] = r.intensity;
+}
+
+} // namespace gem

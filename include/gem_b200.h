@@ -1,0 +1,188 @@
+/*
+ * gem_b200.h -- C ABI of libgem_b200.so: the B200-native (sm_100a) replacement for GEM's
+ * GPU map library `libgpu.so` (reference: elevation_mapping/elevation_mapping/cuda/
+ * gpu_process.cu, "gpu.cu" below; ZJU-Robotics-Lab/GEM @ d7ec953).
+ *
+ * The reference boundary is 9 C++-mangled free functions declared ad hoc by their callers
+ * (ElevationMapping.cpp:44-50, SensorProcessorBase.cpp:34, RobotMotionMapUpdater.cpp:18)
+ * with Eigen types by value and one process-global map.  This header is the C-ABI they bind
+ * to instead: plain pointers and sizes, an opaque per-map handle, int status codes.
+ * compat/gpu_process_shim.cpp re-exports the 9 original symbols on top of it (needs Eigen,
+ * compiled inside the catkin workspace), see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns GEM_OK (0) or a GEM_ERR_* code; gem_last_error() gives text;
+ *   - "device" pointers are CUDA device pointers on the handle's device, "host" pointers
+ *     are ordinary (pageable or pinned) host memory;
+ *   - all work of one handle is ordered on one CUDA stream; functions taking device
+ *     pointers are asynchronous on that stream, functions taking host pointers return
+ *     after the result is visible to the host (like the reference wrappers, which are all
+ *     host-synchronous);
+ *   - a handle is thread-compatible: calls on the same handle must be serialised by the
+ *     caller (the reference node does so with MapMutex_, ElevationMapping.cpp:277,292);
+ *   - there is NO CPU fallback: gem_create fails with GEM_ERR_NO_DEVICE without a GPU.
+ *
+ * Layer layout seen through this ABI is the reference's: row-major L*L arrays, index
+ * x*L+y; elevation/variance/intensity/colour/traver are indexed by STORAGE index (circular
+ * buffer), lowest by GEOGRAPHIC index (gpu.cu:430-431).  Empty cell
+ * sentinels: elevation == -10, variance == -10, traver == -10 (gpu.cu:203-210).
+ */
+#ifndef GEM_B200_H
+#define GEM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEM_B200_VERSION 100
+
+enum {
+    GEM_OK = 0,
+    GEM_ERR_INVALID = 1,   /* bad argument                                   */
+    GEM_ERR_CUDA = 2,      /* CUDA runtime error (text in gem_last_error)    */
+    GEM_ERR_NO_DEVICE = 3, /* no usable CUDA device / kernels not loadable   */
+    GEM_ERR_NOMEM = 4
+};
+
+typedef struct gem_map gem_map; /* opaque */
+
+/* Replaces the arguments of Init_GPU_elevationmap (gpu.cu:940) + the hard-coded knobs. */
+typedef struct gem_config {
+    int length;                  /* cells per side L (gpu.cu:35)                          */
+    float resolution;            /* metres per cell (gpu.cu:36)                           */
+    float mahalanobis_threshold; /* uploaded but unused by the reference (gate is 5)      */
+    float obstacle_threshold;    /* ElevationMapping.cpp:194 hard-codes 0.7               */
+    int compat_box_filter;       /* 1: apply the sensor-frame box filter of gpu.cu:393    */
+    int max_points;              /* per-launch capacity; larger calls are chunked. 0=auto */
+    int device;                  /* CUDA ordinal, -1 = current device                     */
+    void *stream;                /* cudaStream_t to run on; NULL = library-owned stream   */
+    /* spatial tile owned by this handle (multi-GPU tiling).  All zero = whole
+     * map.  Tiled handles do not scroll (gem_move keeps start index 0). */
+    int tile_row0, tile_rows, tile_col0, tile_cols;
+} gem_config;
+
+enum { GEM_SENSOR_LASER = 0, GEM_SENSOR_STRUCTURED_LIGHT = 1 };
+
+/* Sensor noise model: laser = gpu.cu:410-411 (C_min_r, C_beam_a, C_beam_c);
+ * structured light = StructuredLightSensorProcessor.cpp:129-139 (doubles). */
+typedef struct gem_sensor_model {
+    int type;
+    float min_radius, beam_angle, beam_constant;
+    double normal_factor_a, normal_factor_b, normal_factor_c, normal_factor_d, normal_factor_e;
+    double lateral_factor;
+} gem_sensor_model;
+
+/* Per-frame constants = the by-value arguments of Process_points (gpu.cu:1085), derived by
+ * SensorProcessorBase::GPUPointCloudprocess / readcomputerparam (SPB.cpp:171-206,270-290).
+ * Matrices are row-major. */
+typedef struct gem_frame {
+    float T[16];                 /* map <- sensor (Eigen::Matrix4f transform)             */
+    float sensor_jacobian[3];    /* row 3 of R_map<-sensor (SPB.cpp:275)                  */
+    float rotation_variance[9];  /* Sigma_q, all zero in GEM (SPB.cpp:202-204)            */
+    float C_SB_transpose[9];     /* SPB.cpp:283                                           */
+    float P_mul_C_BM_transpose[3]; /* SPB.cpp:282                                         */
+    float B_r_BS_skew[9];        /* SPB.cpp:284                                           */
+    double rel_lower, rel_upper; /* height window, double compare (gpu.cu:397)            */
+    gem_sensor_model sensor;
+} gem_frame;
+
+typedef struct gem_stats {
+    long long points_in;      /* points offered by the last add/process call              */
+    long long points_binned;  /* accepted by the filters AND inside the grid              */
+    long long cells_touched;  /* distinct cells updated by the last add/fuse call         */
+    int max_points_per_cell;  /* longest per-cell sequential fold in the last call        */
+} gem_stats;
+
+/* layer ids for gem_get_layer / gem_set_layer */
+enum {
+    GEM_LAYER_ELEVATION = 0, GEM_LAYER_VARIANCE = 1, GEM_LAYER_INTENSITY = 2,
+    GEM_LAYER_COLOR_R = 3, GEM_LAYER_COLOR_G = 4, GEM_LAYER_COLOR_B = 5,
+    GEM_LAYER_TRAVER = 6, GEM_LAYER_LOWEST = 7, GEM_LAYER_ROUGH = 8, GEM_LAYER_SLOPE = 9
+};
+
+int gem_version(void);
+const char *gem_last_error(const gem_map *m); /* m may be NULL: last create error */
+
+/* Init_GPU_elevationmap (gpu.cu:940-994): allocate layers + scratch, init sentinels. */
+int gem_create(const gem_config *cfg, gem_map **out);
+int gem_destroy(gem_map *m);
+int gem_sync(gem_map *m); /* wait for the handle's stream */
+
+/* Move (gpu.cu:1004-1083): scroll the circular buffer to follow pos[0..1], record
+ * pos[2] as sensorZatLowestScan.  Outputs may be NULL. */
+int gem_move(gem_map *m, const float pos[3], float centre_out[2], int start_out[2],
+             float aligned_shift_out[2]);
+
+/* ---- fused hot path: Process_points + Fuse with device-resident intermediates --------
+ * xyzi: n x float4 {x, y, z, intensity} in the sensor frame; rgba: n x uchar4 {r,g,b,-}
+ * or NULL (colour path off).  Equivalent to SensorProcessorBase::process +
+ * ElevationMapping::processpoints (ElevationMapping.cpp:254-283). */
+int gem_add_points(gem_map *m, const void *xyzi_device, const void *rgba_device, int n,
+                   const gem_frame *frame);
+int gem_add_points_host(gem_map *m, const void *xyzi_host, const void *rgba_host, int n,
+                        const gem_frame *frame);
+/* PCL record ingest: n x 32-byte PointXYZRGBICT {x,y,z,pad, b,g,r,a, covariance, intensity,
+ * travers} (PointXYZRGBICT.hpp:26-48), host memory, e.g. cloud->points.data(). */
+int gem_add_cloud_pcl_host(gem_map *m, const void *points32_host, int n, const gem_frame *frame);
+
+/* ---- unfused reference calls (host arrays, exactly the reference argument meaning) ----
+ * Process_points (gpu.cu:1085-1144): outputs key (storage index or -1), var, x_ts, y_ts,
+ * z_ts; rejected points give -1 in every output (gpu.cu:443-450).  Also updates `lowest`. */
+int gem_process_points(gem_map *m, int *map_index, const float *x, const float *y,
+                       const float *z, float *var, float *x_ts, float *y_ts, float *z_ts,
+                       int n, const gem_frame *frame);
+/* Fuse (gpu.cu:1154-1193) */
+int gem_fuse(gem_map *m, int n, const int *index, const int *R, const int *G, const int *B,
+             const float *intensity, const float *height, const float *var);
+
+/* Mapvar_update (gpu.cu:1146-1152) */
+int gem_var_update(gem_map *m, float var_update);
+
+/* Map_feature (gpu.cu:1256-1302): computes traversability into the map and copies 9
+ * row-major storage-indexed layers to host arrays (any may be NULL). */
+int gem_map_feature(gem_map *m, float *elevation, float *var, int *R, int *G, int *B,
+                    float *rough, float *slope, float *traver, float *intensity);
+/* same computation, no host copies (results stay in the device layers) */
+int gem_compute_features(gem_map *m);
+
+/* Raytracing (gpu.cu:1304-1318): visibility clean-up + reset of `lowest` */
+int gem_raytracing(gem_map *m);
+
+/* Map_optmove (gpu.cu:1215-1233), Map_closeloop (gpu.cu:1235-1254) */
+int gem_opt_move(gem_map *m, const float opt_p[2], float height_update, float aligned_out[2]);
+int gem_closeloop(gem_map *m, const float update_position[2], float height_update);
+
+/* ---- write-back replacing ElevationMap::show's L*L CPU loop (ElevationMap.cpp:85-149) --
+ * Emits 9 float32 layers {elevation, variance, rough, slope, traver, color_r, color_g,
+ * color_b, intensity} (ElevationMap.cpp:44) in grid_map::Matrix layout: COLUMN-major,
+ * storage indexed, NaN where the reference leaves the cell cleared (elevation == -10 or
+ * traver == -10 or traver is NaN, ElevationMap.cpp:101).  host_layers[k] may be NULL. */
+int gem_export_layers(gem_map *m, float *host_layers[9]);
+
+/* raw layer access (row-major L*L, float or int32 for the colour ids) for tests and
+ * checkpoint/restore (the dead G_get_mapinfo/G_set_mapinfo of gpu.cu:457-475). */
+int gem_get_layer(gem_map *m, int layer, void *host_out);
+int gem_set_layer(gem_map *m, int layer, const void *host_in);
+int gem_get_state(gem_map *m, float centre[2], int start[2], float *sensor_z);
+int gem_get_stats(gem_map *m, gem_stats *out);
+
+/* pinned host memory helpers for callers that want async-capable staging */
+int gem_host_alloc(void **out, unsigned long long bytes);
+int gem_host_free(void *p);
+
+/* ---- multi-GPU tiling helpers ---------------------------------------------
+ * gem_route_points: transform n device points like gem_add_points but do not fuse; emit
+ * routed records {key(global geographic linear index), h, var, rgba, intensity} = 20 B
+ * stably bucketed by owning tile (owner = (gx / tile_rows) * tiles_per_row + gy / tile_cols)
+ * into rec_out_device, and the per-owner counts into counts_out_device[n_owners].
+ * gem_fuse_records: fold received records (any owner order, already in global order)
+ * into this handle's tile. */
+int gem_route_points(gem_map *m, const void *xyzi_device, const void *rgba_device, int n,
+                     const gem_frame *frame, int tiles_r, int tiles_c, void *rec_out_device,
+                     int *counts_out_device);
+int gem_fuse_records(gem_map *m, const void *rec_device, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEM_B200_H */

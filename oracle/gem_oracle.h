@@ -1,0 +1,117 @@
+/*
+ * gem_oracle.h -- CPU ORACLE for the GEM point-cloud -> elevation-grid fusion path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may build, link, import or run it.
+ * The product (gem_b200/, include/) never touches anything under oracle/.
+ *
+ * PARITY STATUS: "parity unpinned by the reference's own tests".  The reference
+ * (ZJU-Robotics-Lab/GEM @ d7ec953) ships no tests, no golden vectors and no CPU
+ * implementation of this path; its only statement of the
+ * algorithm is the CUDA file elevation_mapping/elevation_mapping/cuda/gpu_process.cu
+ * ("gpu.cu" below), which needs Eigen and cannot be built in this image from its own
+ * sources alone.  This file restates gpu.cu op-for-op in plain C (fp32 where the
+ * reference is fp32, fp64 where C++ promotion rules make it fp64, no FMA contraction),
+ * and is cross-checked three ways (tests/): a literal O(C*N) twin of G_fuse vs the O(N)
+ * form, an independent numpy float32 re-derivation, and -- when oracle/_ref exists -- the
+ * reference's own kernels compiled from /root/reference against a stand-in Eigen header
+ * and run on the GPU box (oracle/ref_harness.cu).
+ *
+ * Every function cites the reference lines it follows.  Conscious definitions where
+ * the reference is racy / undefined are marked "ORACLE DEFINITION".
+ */
+#ifndef GEM_ORACLE_H
+#define GEM_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_map {
+    int L;                    /* cells per side (gpu.cu:35 Length)            */
+    float res;                /* gpu.cu:36 Resolution                         */
+    float obstacle_threshold; /* gpu.cu:37                                    */
+    float mahalanobis;        /* gpu.cu:56, uploaded but unused (gate is 5)   */
+    /* layers, row-major L*L (gpu.cu:20-28) */
+    float *lowest;            /* indexed by GEOGRAPHIC linear index           */
+    float *elevation, *variance, *intensity, *traver; /* indexed by STORAGE   */
+    int *colorR, *colorG, *colorB;
+    float centre[2];          /* gpu.cu:30 central_coordinate                 */
+    int start[2];             /* gpu.cu:31 start_indice                       */
+    float sensorZ;            /* gpu.cu:33 sensorZatLowestScan                */
+    int compat_box_filter;    /* 1 = hard-coded filter of gpu.cu:393          */
+} orc_map;
+
+/* sensor model selector */
+enum { ORC_SENSOR_LASER = 0, ORC_SENSOR_STRUCTURED_LIGHT = 1 };
+
+typedef struct orc_sensor {
+    int type;
+    /* laser (gpu.cu:410-411, Laser.cpp:134-163) */
+    float min_r, beam_a, beam_c;
+    /* structured light (SL.cpp:129-141), parameters are double in the reference */
+    double nf_a, nf_b, nf_c, nf_d, nf_e, lateral;
+} orc_sensor;
+
+/* gpu.cu:940-994 + G_Init_map :198-214 */
+orc_map *orc_create(int length, float resolution, float mahalanobis, float obstacle_threshold);
+void orc_destroy(orc_map *m);
+
+/* gpu.cu:1004-1083 Move (+ :893-938, :996-1002) */
+void orc_move(orc_map *m, const float pos[3], float centre_out[2], int start_out[2],
+              float shift_out[2]);
+
+/* gpu.cu:309-358: returns geographic linear index or -1; *storage gets PointsToMapIndex */
+int orc_points_to_index(const orc_map *m, float px, float py, int *storage);
+
+/* gpu.cu:1085-1144 Process_points + G_pointsprocess :384-455.
+ * T: row-major 4x4 map<-sensor.  rotVar, C_SB_T, B_skew: row-major 3x3.
+ * Outputs (length n): key (storage index or -1), var, x_ts, y_ts, z_ts (any may be NULL).
+ * Updates m->lowest (ORACLE DEFINITION, see .c). */
+void orc_process_points(orc_map *m, int n, const float *x, const float *y, const float *z,
+                        const float T[16], double relLower, double relUpper,
+                        const orc_sensor *sensor, const float sJ[3], const float rotVar[9],
+                        const float C_SB_T[9], const float P_C_BM_T[3], const float B_skew[9],
+                        int *key, float *var, float *x_ts, float *y_ts, float *z_ts);
+
+/* gpu.cu:1154-1193 Fuse + G_fuse :477-537, O(N) in-order scatter form */
+void orc_fuse(orc_map *m, int n, const int *key, const int *R, const int *G, const int *B,
+              const float *intensity, const float *h, const float *var);
+/* literal O(C*N) twin of G_fuse (one "thread" per cell scanning all points) */
+void orc_fuse_literal(orc_map *m, int n, const int *key, const int *R, const int *G,
+                      const int *B, const float *intensity, const float *h, const float *var);
+
+/* gpu.cu:1146-1152 + :540-547 */
+void orc_var_update(orc_map *m, float dv);
+
+/* gpu.cu:1256-1302 + G_Mapfeature :549-670 + computerEigenvalue :66-187.
+ * Output arrays are STORAGE indexed, length L*L.  For empty cells the reference leaves
+ * rough/slope/traver outputs uninitialised; ORACLE DEFINITION: rough=0, slope=0, traver=-10
+ * in the OUTPUT arrays (map state traver is left stale exactly like the reference). */
+void orc_map_feature(orc_map *m, float *elevation, float *var, int *R, int *G, int *B,
+                     float *rough, float *slope, float *traver, float *intensity);
+
+/* gpu.cu:1304-1318 + G_Raytracing :708-891 + G_Clear_maplowest :232-239 */
+void orc_raytracing(orc_map *m);
+
+/* gpu.cu:1215-1233, :1235-1254 */
+void orc_optmove(orc_map *m, const float opt_p[2], float height_update, float aligned_out[2]);
+void orc_closeloop(orc_map *m, const float update_position[2], float height_update);
+
+/* deterministic float trig used by the feature kernel restatement (see .c) */
+float orc_sinf(float a);
+float orc_cosf(float a);
+float orc_atan2f(float y, float x);
+float orc_acosf(float x);
+
+/* multi-threaded twin used only as the CPU baseline timer (bench.py cpu_baseline):
+ * process_points + fuse over nthreads, cells partitioned by storage row range so the
+ * per-cell order is preserved.  Result identical to the single-thread path. */
+void orc_add_points_mt(orc_map *m, int n, const float *xyzi /* n*4 */, const unsigned char *rgba /* n*4 or NULL */,
+                       const float T[16], double relLower, double relUpper,
+                       const orc_sensor *sensor, const float sJ[3], int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,298 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): cell indices bit-exact; fused height/variance within 1e-5
+relative.  Because the library is compiled without FMA contraction and shares the oracle's
+arithmetic definition, the tests assert the stronger property: every layer bit-identical.
+"""
+import numpy as np
+import pytest
+
+import gem_b200
+from gem_b200 import synth
+from helpers import assert_layers_equal, split_rgb
+from oracle_lib import OracleMap
+
+pytestmark = pytest.mark.gpu
+
+
+def laser_frame(T, base_z=0.0, **kw):
+    return gem_b200.make_frame(T, gem_b200.LaserSensorProcessor(), base_z=base_z, **kw)
+
+
+def both(L, res, **kw):
+    return gem_b200.ElevationMap(L, res, **kw), OracleMap(L, res, **{k: v for k, v in kw.items() if k != "max_points"})
+
+
+def test_process_points_bit_exact_c1():
+    """BASELINE config 1: one 64-beam frame into 200x200 @ 0.1 m; keys/var/height bit-exact."""
+    fr = synth.hdl64_frame(0)
+    g, o = both(200, 0.1, compat_box_filter=False)
+    f = laser_frame(fr["T"], base_z=0.0)
+    g.move(fr["position"]); o.move(fr["position"])
+    x, y, z = (fr["xyzi"][:, k].copy() for k in range(3))
+    kg = g.process_points(x, y, z, f)
+    ko = o.process_points(x, y, z, f)
+    names = ["map_index", "var", "x_ts", "y_ts", "z_ts"]
+    for a, b, nm in zip(kg, ko, names):
+        assert a.dtype == b.dtype
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), nm
+    assert (kg[0] >= 0).sum() > 10000
+    assert_layers_equal(g, o, ["lowest"], what="process_points")
+
+
+def test_fused_add_c1_all_layers():
+    fr = synth.hdl64_frame(0)
+    g, o = both(200, 0.1, compat_box_filter=False)
+    f = laser_frame(fr["T"])
+    g.move(fr["position"]); o.move(fr["position"])
+    g.add(fr["xyzi"], fr["rgba"], f)
+    o.add(fr["xyzi"], fr["rgba"], f)
+    assert_layers_equal(g, o, what="c1 add")
+    st = g.stats()
+    assert st["points_in"] == fr["xyzi"].shape[0]
+    assert 0 < st["points_binned"] <= st["points_in"]
+    assert st["cells_touched"] == int((o.get_layer("elevation") != -10).sum())
+
+
+def test_unfused_equals_fused():
+    fr = synth.hdl64_frame(1)
+    f = laser_frame(fr["T"])
+    g1 = gem_b200.ElevationMap(200, 0.1, compat_box_filter=False)
+    g2 = gem_b200.ElevationMap(200, 0.1, compat_box_filter=False)
+    g1.move(fr["position"]); g2.move(fr["position"])
+    g1.add(fr["xyzi"], fr["rgba"], f)
+    x, y, z = (fr["xyzi"][:, k].copy() for k in range(3))
+    key, var, xt, yt, zt = g2.process_points(x, y, z, f)
+    R, G, B = split_rgb(fr["rgba"])
+    g2.fuse_points(key, R, G, B, fr["xyzi"][:, 3], zt, var)
+    assert_layers_equal(g1, g2, what="fused vs unfused")
+
+
+def test_order_dependence_dense_collisions():
+    """many points per cell, gate hits, replacements: the per-cell order must be index order"""
+    L, res = 64, 0.25
+    c = synth.random_cloud(60000, seed=7, extent=7.5, zmin=-1.0, zmax=2.0)
+    T = synth.pose_matrix(0.3, -0.2, 0.5, 0.3)
+    f = laser_frame(T, base_z=0.5)
+    g, o = both(L, res, compat_box_filter=False)
+    for m in (g, o):
+        m.move([0.3, -0.2, 0.5])
+        m.add(c["xyzi"], c["rgba"], f)
+    assert_layers_equal(g, o, what="dense")
+    assert g.stats()["max_points_per_cell"] > 20
+
+
+def test_very_long_cell_lists_fallback_paths():
+    """> 1024 points in one cell exercises the global-memory selection path of k_fold"""
+    L, res = 32, 0.5
+    rng = np.random.default_rng(3)
+    n = 5000
+    xyz = np.zeros((n, 3), np.float32)
+    xyz[:3000, :2] = rng.uniform(0.01, 0.49, (3000, 2))      # one cell, 3000 points
+    xyz[3000:, :2] = rng.uniform(-7, 7, (2000, 2))
+    xyz[:, 2] = rng.uniform(-0.5, 0.5, n)
+    xyzi = np.concatenate([xyz, rng.integers(1, 255, (n, 1)).astype(np.float32)], 1).astype(np.float32)
+    rgba = rng.integers(1, 255, (n, 4)).astype(np.uint8)
+    f = laser_frame(np.eye(4), base_z=0.0)
+    g, o = both(L, res, compat_box_filter=False)
+    for m in (g, o):
+        m.add(xyzi, rgba, f)
+    assert_layers_equal(g, o, what="long lists")
+    assert g.stats()["max_points_per_cell"] >= 3000
+
+
+def test_compat_box_filter_and_thresholds():
+    fr = synth.hdl64_frame(2, compat_axes=True)
+    g, o = both(200, 0.1, compat_box_filter=True)
+    f = laser_frame(fr["T"], base_z=0.0)
+    for m in (g, o):
+        m.move(fr["position"])
+        m.add(fr["xyzi"], fr["rgba"], f)
+    assert_layers_equal(g, o, what="box filter")
+    n_valid = int((o.get_layer("elevation") != -10).sum())
+    assert 0 < n_valid
+
+
+def test_multi_frame_stream_with_scroll_and_cleanup():
+    """10-frame stream: move -> add -> var_update -> features -> raytracing, layers after every frame"""
+    L, res = 256, 0.1
+    scene = synth.make_scene()
+    g, o = both(L, res, compat_box_filter=False)
+    for k in range(10):
+        fr = synth.hdl64_frame(k, scene=scene, speed=7.0)
+        f = laser_frame(fr["T"])
+        for m in (g, o):
+            m.move(fr["position"])
+            m.add(fr["xyzi"], fr["rgba"], f)
+            m.var_update(0.0)
+        assert_layers_equal(g, o, what=f"frame {k} after add")
+        fg = g.map_feature()
+        fo = o.map_feature()
+        for name in fo:
+            a, b = fg[name], fo[name]
+            same = (a == b) | (np.isnan(a.astype(np.float64)) & np.isnan(b.astype(np.float64)))
+            assert same.all(), f"frame {k} map_feature {name}: {np.count_nonzero(~same)} differ"
+        assert_layers_equal(g, o, ["traver"], what=f"frame {k} traver")
+        g.raytracing(); o.raytracing()
+        assert_layers_equal(g, o, what=f"frame {k} after raytracing")
+        sg, so = g.state(), o.state()
+        assert np.array_equal(sg[0], so[0]) and np.array_equal(sg[1], so[1]) and sg[2] == so[2]
+    assert (o.get_layer("elevation") != -10).sum() > 1000
+
+
+def test_structured_light_c3_small():
+    fr = synth.d435_frame(0)
+    sp = gem_b200.StructuredLightSensorProcessor()
+    f = gem_b200.make_frame(fr["T"], sp, base_z=0.0)
+    g, o = both(512, 0.02, compat_box_filter=False)
+    for m in (g, o):
+        m.move(fr["position"])
+        m.add(fr["xyzi"], fr["rgba"], f)
+    assert_layers_equal(g, o, what="structured light")
+    assert (o.get_layer("elevation") != -10).sum() > 5000
+
+
+def test_rotation_variance_term():
+    c = synth.random_cloud(20000, seed=11, extent=9.0)
+    T = synth.pose_matrix(0.0, 0.0, 0.0, 0.7)
+    rv = np.diag([1e-4, 2e-4, 3e-4]).astype(np.float32)
+    rv[0, 1] = rv[1, 0] = 5e-5
+    csb = synth.pose_matrix(0, 0, 0, 0.2)[:3, :3].T
+    f = laser_frame(T, rotation_variance=rv, C_SB_transpose=csb, P_mul_C_BM_transpose=[0.01, -0.02, 0.99],
+                    B_r_BS_skew=[0, -0.3, 0.1, 0.3, 0, -0.2, -0.1, 0.2, 0])
+    g, o = both(200, 0.1, compat_box_filter=False)
+    for m in (g, o):
+        m.add(c["xyzi"], c["rgba"], f)
+    assert_layers_equal(g, o, what="rotation variance")
+
+
+def test_odd_length_and_edges():
+    c = synth.random_cloud(30000, seed=5, extent=8.0)
+    f = laser_frame(np.eye(4))
+    for L in (75, 120):
+        g, o = both(L, 0.2, compat_box_filter=False)
+        for m in (g, o):
+            m.move([0.37, -1.21, 0.0])
+            m.add(c["xyzi"], c["rgba"], f)
+        assert_layers_equal(g, o, what=f"L={L}")
+
+
+def test_empty_and_ragged_inputs():
+    g, o = both(64, 0.1, compat_box_filter=False)
+    f = laser_frame(np.eye(4))
+    empty = np.zeros((0, 4), np.float32)
+    g.add(empty, None, f, n=0)
+    o.fuse_points(np.zeros(0, np.int32), None, None, None, None, np.zeros(0, np.float32), np.zeros(0, np.float32))
+    assert_layers_equal(g, o, what="empty")   # variance floor applied to every cell by the empty fuse
+    c = synth.random_cloud(1, seed=1, extent=1.0)
+    for m in (g, o):
+        m.add(c["xyzi"], None, f)
+    assert_layers_equal(g, o, what="single point, no colour")
+    nanpts = np.full((5, 4), np.nan, np.float32)
+    for m in (g, o):
+        m.add(nanpts, None, f)
+    assert_layers_equal(g, o, what="NaN points")
+
+
+def test_chunking_preserves_order():
+    c = synth.random_cloud(50000, seed=21, extent=6.0)
+    f = laser_frame(np.eye(4))
+    g = gem_b200.ElevationMap(64, 0.2, compat_box_filter=False, max_points=4096)
+    o = OracleMap(64, 0.2, compat_box_filter=False)
+    g.add(c["xyzi"], c["rgba"], f)
+    o.add(c["xyzi"], c["rgba"], f)
+    assert_layers_equal(g, o, ["elevation", "variance", "intensity", "color_r", "color_g", "color_b"], what="chunked")
+
+
+def test_device_pointer_path_matches_host_path():
+    import torch
+    fr = synth.hdl64_frame(3)
+    f = laser_frame(fr["T"])
+    g1 = gem_b200.ElevationMap(200, 0.1, compat_box_filter=False)
+    g2 = gem_b200.ElevationMap(200, 0.1, compat_box_filter=False)
+    xyzi = torch.from_numpy(fr["xyzi"]).cuda()
+    rgba = torch.from_numpy(fr["rgba"]).cuda()
+    torch.cuda.synchronize()
+    g1.move(fr["position"]); g2.move(fr["position"])
+    g1.add(xyzi, rgba, f)
+    g1.sync()
+    g2.add(fr["xyzi"], fr["rgba"], f)
+    assert_layers_equal(g1, g2, what="device vs host input")
+    assert g1.stats() == g2.stats()
+
+
+def test_pcl_record_ingest():
+    fr = synth.hdl64_frame(4)
+    n = fr["xyzi"].shape[0]
+    rec = np.zeros((n, 8), np.float32)
+    rec[:, 0:3] = fr["xyzi"][:, :3]
+    bgra = (fr["rgba"][:, 2].astype(np.uint32) | (fr["rgba"][:, 1].astype(np.uint32) << 8) |
+            (fr["rgba"][:, 0].astype(np.uint32) << 16))
+    rec[:, 4] = bgra.view(np.float32)
+    rec[:, 6] = fr["xyzi"][:, 3]
+    f = laser_frame(fr["T"])
+    g1 = gem_b200.ElevationMap(200, 0.1, compat_box_filter=False)
+    g2 = gem_b200.ElevationMap(200, 0.1, compat_box_filter=False)
+    g1.add_pcl(rec, f)
+    g2.add(fr["xyzi"], fr["rgba"], f)
+    assert_layers_equal(g1, g2, what="pcl ingest")
+
+
+def test_export_layers_matches_show_masking():
+    fr = synth.hdl64_frame(0)
+    f = laser_frame(fr["T"])
+    g, o = both(200, 0.1, compat_box_filter=False)
+    for m in (g, o):
+        m.move(fr["position"])
+        m.add(fr["xyzi"], fr["rgba"], f)
+    eo = o.export_layers()
+    g.compute_features()
+    eg = g.export_layers()
+    for name in eo:
+        a, b = eg[name], eo[name]
+        assert a.flags["F_CONTIGUOUS"]
+        same = (a == b) | (np.isnan(a) & np.isnan(b))
+        assert same.all(), name
+
+
+def test_opt_move_closeloop_var_update():
+    c = synth.random_cloud(20000, seed=2, extent=6.0)
+    f = laser_frame(np.eye(4))
+    g, o = both(128, 0.1, compat_box_filter=False)
+    for m in (g, o):
+        m.add(c["xyzi"], c["rgba"], f)
+        m.var_update(0.002)
+        a = m.opt_move([0.33, -0.48], 0.05)
+        m.closeloop([1.02, 0.51], -0.02)
+        m.add(c["xyzi"][:5000], c["rgba"][:5000], f)
+        m.var_update(-0.0015)
+        m.add(c["xyzi"][5000:7000], c["rgba"][5000:7000], f)
+    assert_layers_equal(g, o, what="optmove/closeloop/var_update")
+    assert np.array_equal(g.state()[0], o.state()[0])
+
+
+def test_headline_config_properties_c2():
+    """BASELINE config 2 at full size (1024x1024 @ 0.05 m): oracle comparison on 3 frames plus
+    size-independent properties: permutation across cells is invariant, idempotent re-export."""
+    scene = synth.make_scene()
+    g, o = both(1024, 0.05, compat_box_filter=False)
+    for k in range(3):
+        fr = synth.hdl64_frame(k, scene=scene)
+        f = laser_frame(fr["T"])
+        for m in (g, o):
+            m.move(fr["position"])
+            m.add(fr["xyzi"], fr["rgba"], f)
+    assert_layers_equal(g, o, what="c2")
+    # permutation that keeps the relative order inside every cell must not change anything
+    fr = synth.hdl64_frame(3, scene=scene)
+    f = laser_frame(fr["T"])
+    g2 = gem_b200.ElevationMap(1024, 0.05, compat_box_filter=False)
+    g3 = gem_b200.ElevationMap(1024, 0.05, compat_box_filter=False)
+    g2.move(fr["position"]); g3.move(fr["position"])
+    x, y, z = (fr["xyzi"][:, k].copy() for k in range(3))
+    key = g2.process_points(x, y, z, f)[0]
+    g2.raytracing()  # reset lowest, the dry run above touched it
+    perm = np.argsort(key, kind="stable")  # groups cells together, stable inside each cell
+    g2.add(fr["xyzi"], fr["rgba"], f)
+    g3.add(np.ascontiguousarray(fr["xyzi"][perm]), np.ascontiguousarray(fr["rgba"][perm]), f)
+    assert_layers_equal(g2, g3, ["elevation", "variance", "intensity", "color_r", "color_g", "color_b"], what="perm")
