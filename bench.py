@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the GEM point-cloud -> elevation-grid fusion hot path.
+
+Metric (BASELINE.json): Mpoints/s fused into a 1024x1024 @ 0.05 m grid, and the achieved
+fraction of the HBM roofline.  One "step" = one sensor frame through the hot path:
+gem_move (scroll) + gem_add_points (transform + variance + bin + per-cell Kalman fold).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N == 1 : BASELINE configs[1] (HDL-64E-shaped 10 Hz stream, 1024x1024 @ 0.05 m, 1 x B200).
+N  > 1 : launched by torchrun, one rank per GPU: one sensor per rank, the global map tiled
+         across ranks, points routed to their owning tile with one NCCL all-to-all
+         (BASELINE configs[3]/[4] shape; weak scaling: per-GPU points fixed).
+--impl reference : the reference has no CPU implementation of this path and its CUDA file
+         cannot be built here (needs Eigen), so the reference arm times the CPU
+         oracle (oracle/gem_oracle.c, a restatement of the reference semantics) on all host
+         threads, kind "port".
+
+Prints exactly one JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_POINT = 44  # 16 B float4 in + 4 B rgba + 16 B elev/var RMW + 8 B colour/intensity write
+L2_BYTES = 126e6
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic stream
+# ------------------------------------------------------------------------------------------
+def _gen_one(k):
+    from gem_b200 import synth
+    fr = synth.hdl64_frame(k, scene=synth.make_scene())
+    return k, fr
+
+
+def gen_frames(nframes: int, first: int = 0):
+    """frames first..first+nframes-1 of the HDL-64E stream, generated on the host cores"""
+    from concurrent.futures import ProcessPoolExecutor
+    workers = max(1, min(os.cpu_count() or 1, 32, nframes))
+    ks = list(range(first, first + nframes))
+    if workers == 1:
+        out = [_gen_one(k) for k in ks]
+    else:
+        with ProcessPoolExecutor(workers) as ex:
+            out = list(ex.map(_gen_one, ks))
+    out.sort(key=lambda t: t[0])
+    return [fr for _, fr in out]
+
+
+def pingpong(step: int, nframes: int) -> int:
+    """0,1,..,F-1,F-2,..,1,0,1,... keeps consecutive poses 1 m apart for any number of steps"""
+    if nframes == 1:
+        return 0
+    period = 2 * nframes - 2
+    r = step % period
+    return r if r < nframes else period - r
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """samples SM clock and throttle reasons of one GPU while the timed regions run"""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index: int = 0, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, util))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        mhz = [m for m, _ in self.samples]
+        return {"sm_mhz": float(np.median(mhz)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(mhz)}
+
+
+# ------------------------------------------------------------------------------------------
+def laser_frame(fr):
+    import gem_b200
+    return gem_b200.make_frame(fr["T"], gem_b200.LaserSensorProcessor(), base_z=0.0)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic(kernel: str):
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+def cpu_baseline(frames, nsteps: int, threads: int, L: int, res: float):
+    """CPU oracle (restatement of the reference semantics; the reference ships no CPU path) on
+    `threads` host threads over the same stream.  Returns (Mpoints/s, ms/frame, n_frames)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import OracleMap
+    o = OracleMap(L, res, compat_box_filter=False)
+    F = len(frames)
+    fobjs = [laser_frame(fr) for fr in frames]
+    for s in range(min(3, nsteps)):  # warm-up
+        k = pingpong(s, F)
+        o.move(frames[k]["position"])
+        o.add_mt(frames[k]["xyzi"], frames[k]["rgba"], fobjs[k], threads)
+    pts = 0
+    t0 = time.perf_counter()
+    for s in range(nsteps):
+        k = pingpong(3 + s, F)
+        o.move(frames[k]["position"])
+        o.add_mt(frames[k]["xyzi"], frames[k]["rgba"], fobjs[k], threads)
+        pts += frames[k]["xyzi"].shape[0]
+    dt = time.perf_counter() - t0
+    o.close()
+    return pts / dt / 1e6, dt / nsteps * 1e3, nsteps
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    L, res = 1024, 0.05
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    threads = min(os.cpu_count() or 1, 64)
+    F = max(2, min(args.steps + args.warmup + 3, 16))
+    frames = gen_frames(F)
+    nsteps = max(1, args.steps)
+    # bound the run: one step = one frame, ~3-30 ms on the host
+    o_val, ms, n = cpu_baseline(frames, nsteps, threads, L, res)
+    ppf = float(np.mean([f["xyzi"].shape[0] for f in frames]))
+    line = {
+        "impl": "reference", "metric": "Mpoints/s fused into 1024x1024@0.05m grid", "value": o_val,
+        "unit": "Mpoints/s", "n_gpus": args.gpus, "steps": n, "warmup": 3, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: HDL-64E-shaped synthetic 10 Hz stream into 1024x1024@0.05m map",
+                   "points_per_frame": ppf, "note": "reference ships no CPU path and gpu_process.cu cannot be built "
+                   "here (Eigen); this arm times the CPU oracle port of its semantics"},
+        "cpu_baseline": {"value": o_val, "unit": "Mpoints/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} frames of the c2 stream, process_points+fuse, {threads} threads"},
+        "e2e": {"value": o_val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    return line
+
+
+# ------------------------------------------------------------------------------------------
+def run_single(args):
+    import torch
+    import gem_b200
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    L, res = 1024, 0.05
+    K, W = args.steps, args.warmup
+    F = int(min(max(K + W + 2, 8), args.frames))
+    frames = gen_frames(F)
+    fobjs = [laser_frame(fr) for fr in frames]
+    npts = [fr["xyzi"].shape[0] for fr in frames]
+    in_bytes = sum(n * 20 for n in npts)
+    stream = torch.cuda.current_stream()
+    m = gem_b200.ElevationMap(L, res, compat_box_filter=False, stream=stream.cuda_stream)
+    xyzi_d = [torch.from_numpy(fr["xyzi"]).to(dev) for fr in frames]
+    rgba_d = [torch.from_numpy(fr["rgba"]).to(dev) for fr in frames]
+    xyzi_h = [torch.from_numpy(fr["xyzi"]).pin_memory() for fr in frames]
+    rgba_h = [torch.from_numpy(fr["rgba"]).pin_memory() for fr in frames]
+    pos = [fr["position"] for fr in frames]
+    flush = torch.empty(int(256e6), dtype=torch.uint8, device=dev) if in_bytes < 1.2 * L2_BYTES else None
+
+    def step(s):
+        k = pingpong(s, F)
+        m.move(pos[k])
+        m.add(xyzi_d[k], rgba_d[k], fobjs[k], n=npts[k])
+        return npts[k]
+
+    sampler = ClockSampler(0).start()
+    # pre-populate the map + W untimed warm-up steps
+    s0 = 0
+    for s in range(10 + W):
+        step(s0); s0 += 1
+    torch.cuda.synchronize()
+
+    # ---- timed region: device-resident inputs ------------------------------------------------
+    m.profile_read(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pts = 0
+    if flush is None:
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for s in range(K):
+            pts += step(s0 + s)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_total = e0.elapsed_time(e1)
+    else:
+        # inputs smaller than L2: flush L2 between steps and sum per-step event times
+        ms_total = 0.0
+        for s in range(K):
+            flush.fill_(s & 255)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            pts += step(s0 + s)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms_total += e0.elapsed_time(e1)
+    launches = m.profile_read(reset=True)["launches"]
+    s0 += K
+    value = pts / (ms_total * 1e-3) / 1e6
+
+    # ---- per-kernel durations (separate pass: event bracketing perturbs the timeline) ----------
+    Kp = min(K, 200)
+    m.profile_enable(True)
+    ppts = 0
+    for s in range(Kp):
+        ppts += step(s0 + s)
+    prof = m.profile_read(reset=True)
+    m.profile_enable(False)
+    s0 += Kp
+    add_classes = ["transform_bin", "alloc_cells", "scatter", "fold", "clear_floor"]
+    dom = max(add_classes, key=lambda c: prof["ms"][c])
+    dom_avg_ms = prof["ms"][dom] / max(1, prof["count"][dom])
+    peak, peak_src = load_peaks()
+    algo_bytes = ALGO_BYTES_PER_POINT * (ppts / Kp)
+    achieved = algo_bytes / (dom_avg_ms * 1e-3) / 1e9
+    step_ms_prof = sum(prof["ms"][c] for c in add_classes) / Kp
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": load_traffic("k_" + {"transform_bin": "transform_bin", "alloc_cells": "alloc_cells",
+                                        "scatter": "scatter", "fold": "fold", "clear_floor": "clear_range"}[dom]),
+        "kernel": dom, "kernel_avg_us": dom_avg_ms * 1e3, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": algo_bytes,
+        "whole_step": {"achieved": algo_bytes / (ms_total / K * 1e-3) / 1e9,
+                       "frac": algo_bytes / (ms_total / K * 1e-3) / 1e9 / peak},
+        "kernel_share_of_step": {c: prof["ms"][c] / max(1e-12, sum(prof["ms"][x] for x in add_classes)) for c in add_classes},
+        "kernel_us_per_step": {c: prof["ms"][c] / Kp * 1e3 for c in add_classes},
+    }
+
+    # ---- e2e: host (pinned) buffers through the public API, H2D + D2H inside the timed region ------
+    Ke = K
+    for s in range(min(W, 5)):
+        k = pingpong(s0, F); m.move(pos[k]); m.add(xyzi_h[k].numpy(), rgba_h[k].numpy(), fobjs[k]); s0 += 1
+    torch.cuda.synchronize()
+    epts = 0
+    xh = [t.numpy() for t in xyzi_h]
+    rh = [t.numpy() for t in rgba_h]
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for s in range(Ke):
+        k = pingpong(s0 + s, F)
+        m.move(pos[k])
+        m.add(xh[k], rh[k], fobjs[k])   # gem_add_points_host: H2D 20 B/pt, kernels, D2H counters, sync
+        epts += npts[k]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    s0 += Ke
+    e2e = {"value": epts / (e2e_ms * 1e-3) / 1e6, "unit": "Mpoints/s",
+           "h2d_bytes_per_step": 20.0 * epts / Ke, "d2h_bytes_per_step": 16,
+           "api": "gem_move + gem_add_points_host (pinned host xyzi+rgba in, stats counters out)"}
+
+    # ---- whole frame incl. features + ray clean-up + grid_map write-back (secondary) --------------
+    Kf = min(K, 20)
+    ex = {n: np.empty((L, L), np.float32, order="F") for n in gem_b200._lib.EXPORT_LAYERS}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(Kf):
+        k = pingpong(s0 + s, F)
+        m.move(pos[k]); m.add(xyzi_d[k], rgba_d[k], fobjs[k], n=npts[k])
+        m.var_update(0.0); m.compute_features(); m.export_layers(ex); m.raytracing()
+    torch.cuda.synchronize()
+    frame_ms = (time.perf_counter() - t0) * 1e3 / Kf
+    clocks = sampler.stop()
+
+    # ---- CPU baseline beside it (bounded sample) ----------------------------------------------------
+    threads = min(os.cpu_count() or 1, 64)
+    nb = int(min(max(K, 5), 40))
+    cb_val, cb_ms, cb_n = cpu_baseline(frames[: min(F, 16)], nb, threads, L, res)
+    cb1_val, _, _ = cpu_baseline(frames[: min(F, 16)], min(nb, 10), 1, L, res)
+
+    st = m.stats()
+    line = {
+        "metric": "Mpoints/s fused into 1024x1024@0.05m grid", "value": value, "unit": "Mpoints/s", "n_gpus": 1,
+        "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: HDL-64E-shaped synthetic 10 Hz stream into 1024x1024@0.05m robot-centric map, 1xB200",
+                   "step": "gem_move + gem_add_points on one frame (device-resident float4 xyzi + uchar4 rgba)",
+                   "points_per_frame": float(np.mean(npts)), "distinct_frames": F,
+                   "l2": (f"inputs larger than L2: {F} distinct frames = {in_bytes/1e6:.0f} MB cycled" if flush is None
+                          else "L2 flushed (256 MB write) between timed steps"),
+                   "box_filter": "off (SURVEY 8d documented deviation)", "colour_path": True},
+        "roofline": roofline,
+        "cpu_baseline": {"value": cb_val, "unit": "Mpoints/s", "cores": threads, "kind": "port",
+                         "sample": f"{cb_n} frames of the same stream, oracle process_points+fuse on {threads} threads; "
+                                   f"single thread: {cb1_val:.1f} Mpoints/s", "single_thread_value": cb1_val},
+        "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+        "extra": {"frame_ms_full_pipeline": frame_ms,
+                  "frame_pipeline": "move+add+var_update+features+export(9 layers D2H)+raytracing, host-synchronous",
+                  "last_frame_stats": st, "host_cores": os.cpu_count()},
+    }
+    return line
+
+
+# ------------------------------------------------------------------------------------------
+def run_tiled(args):
+    from gem_b200 import tiled
+    return tiled.bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, ALGO_BYTES_PER_POINT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="gem_b200", choices=["gem_b200", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="distinct synthetic frames cycled (64 x 2.5 MB > L2)")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        line = run_reference(args)
+    elif args.gpus > 1 or world > 1:
+        line = run_tiled(args)
+    else:
+        line = run_single(args)
+    if line is not None:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

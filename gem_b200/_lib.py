@@ -51,6 +51,12 @@ class GemStats(C.Structure):
                 ("max_points_per_cell", C.c_int)]
 
 
+class GemProfile(C.Structure):
+    _fields_ = [("launches", C.c_longlong), ("ms", C.c_double * 8), ("count", C.c_longlong * 8)]
+
+
+PROF_CLASSES = ["transform_bin", "alloc_cells", "scatter", "fold", "clear_floor", "features", "raytrace", "other"]
+
 # every symbol include/gem_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _FP = C.POINTER(C.c_float)
@@ -78,6 +84,8 @@ SYMBOLS = {
     "gem_set_layer": (C.c_int, [_P, C.c_int, _P]),
     "gem_get_state": (C.c_int, [_P, _FP, _IP, _FP]),
     "gem_get_stats": (C.c_int, [_P, C.POINTER(GemStats)]),
+    "gem_profile_enable": (C.c_int, [_P, C.c_int]),
+    "gem_profile_read": (C.c_int, [_P, C.POINTER(GemProfile), C.c_int]),
     "gem_host_alloc": (C.c_int, [C.POINTER(_P), C.c_ulonglong]),
     "gem_host_free": (C.c_int, [_P]),
     "gem_route_points": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame), C.c_int, C.c_int, _P, _P]),

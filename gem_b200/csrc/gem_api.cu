@@ -56,6 +56,14 @@ struct gem_map {
     gem_stats stats{};
     std::string err;
     std::vector<void *> allocs;
+    // launch accounting / optional per-kernel CUDA-event timing (gem_profile_*)
+    long long launches = 0;
+    bool profiling = false;
+    struct Span { int cls; cudaEvent_t e0, e1; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> free_events;
+    double prof_ms[GEM_PROF_CLASSES] = {0};
+    long long prof_count[GEM_PROF_CLASSES] = {0};
 };
 
 namespace {
@@ -65,6 +73,33 @@ int fail(gem_map *m, int code, const std::string &msg)
     if (m) m->err = msg; else g_create_error = msg;
     return code;
 }
+
+cudaEvent_t prof_event(gem_map *m)
+{
+    if (!m->free_events.empty()) {
+        cudaEvent_t e = m->free_events.back();
+        m->free_events.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+// every kernel launch of the library goes through this macro: counts the launch and, when
+// profiling is on, brackets it with CUDA events on the handle's stream
+#define GEM_LAUNCH(m, cls, ...)                                  \
+    do {                                                         \
+        (m)->launches++;                                         \
+        if ((m)->profiling) {                                    \
+            gem_map::Span sp__{(cls), prof_event(m), prof_event(m)}; \
+            cudaEventRecord(sp__.e0, (m)->stream);               \
+            __VA_ARGS__;                                         \
+            cudaEventRecord(sp__.e1, (m)->stream);               \
+            (m)->spans.push_back(sp__);                          \
+        } else {                                                 \
+            __VA_ARGS__;                                         \
+        }                                                        \
+    } while (0)
 
 #define GEM_CUDA(m, expr)                                                                      \
     do {                                                                                       \
@@ -131,12 +166,12 @@ int flush_pending_floor(gem_map *m)
 {
     for (const Region &r : m->pending) {
         if (r.kind == 0) {
-            k_floor_range<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, 0, m->nc);
+            GEM_LAUNCH(m, GEM_PROF_CLEAR, k_floor_range<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, 0, m->nc));
         } else if (r.kind == 1) {
             const size_t cnt = (size_t)r.n * m->L;
-            k_floor_range<<<blocks_for(cnt, 256), 256, 0, m->stream>>>(m->ml, (size_t)r.start * m->L, cnt);
+            GEM_LAUNCH(m, GEM_PROF_CLEAR, k_floor_range<<<blocks_for(cnt, 256), 256, 0, m->stream>>>(m->ml, (size_t)r.start * m->L, cnt));
         } else {
-            k_floor_cols<<<blocks_for((size_t)r.n * m->L, 256), 256, 0, m->stream>>>(m->ml, m->L, r.start, r.n);
+            GEM_LAUNCH(m, GEM_PROF_CLEAR, k_floor_cols<<<blocks_for((size_t)r.n * m->L, 256), 256, 0, m->stream>>>(m->ml, m->L, r.start, r.n));
         }
     }
     m->pending.clear();
@@ -148,10 +183,10 @@ int flush_pending_floor(gem_map *m)
 template <int ATTR>
 int run_group_fold(gem_map *m, const AttrInput &a, int n, bool do_fuse, bool do_lowest)
 {
-    k_alloc_cells<<<blocks_for((size_t)n, 256, 148 * 4), 256, 0, m->stream>>>(m->sc);
-    k_scatter<ATTR><<<blocks_for((size_t)n, 256, 1 << 30), 256, 0, m->stream>>>(a, n, m->sc);
+    GEM_LAUNCH(m, GEM_PROF_ALLOC, k_alloc_cells<<<blocks_for((size_t)n, 256, 148 * 4), 256, 0, m->stream>>>(m->sc));
+    GEM_LAUNCH(m, GEM_PROF_SCATTER, k_scatter<ATTR><<<blocks_for((size_t)n, 256, 1 << 30), 256, 0, m->stream>>>(a, n, m->sc));
     const int fb = blocks_for((size_t)n, FOLD_WARPS, 148 * 9);
-    k_fold<<<fb, FOLD_WARPS * 32, 0, m->stream>>>(m->geom, m->ml, m->sc, do_fuse ? 1 : 0, do_lowest ? 1 : 0);
+    GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<fb, FOLD_WARPS * 32, 0, m->stream>>>(m->geom, m->ml, m->sc, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }
@@ -211,8 +246,8 @@ template <int IN, int ATTR>
 int add_chunk(gem_map *m, const PointInput &in, const AttrInput &a, int n, const FrameParams &fp)
 {
     GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
-    k_transform_bin<IN><<<blocks_for((size_t)n, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, fp, in, n, m->sc,
-                                                                                 nullptr, nullptr, nullptr);
+    GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin<IN><<<blocks_for((size_t)n, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, fp, in, n, m->sc,
+                                                                                 nullptr, nullptr, nullptr));
     return run_group_fold<ATTR>(m, a, n, true, true);
 }
 
@@ -305,10 +340,10 @@ int gem_create(const gem_config *cfg, gem_map **out)
     e = cudaHostAlloc((void **)&m->h_ctr, sizeof(Counters), cudaHostAllocDefault);
     if (e != cudaSuccess) { m->err = cudaGetErrorString(e); return bail(GEM_ERR_CUDA); }
     // G_Init_map gpu.cu:198-214
-    k_clear_range<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml, 0, nc, 2);
-    k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.rough, nc, 0.0f);
-    k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.slope, nc, 0.0f);
-    k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.traver_out, nc, -10.0f);
+    GEM_LAUNCH(m, GEM_PROF_CLEAR, k_clear_range<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml, 0, nc, 2));
+    GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.rough, nc, 0.0f));
+    GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.slope, nc, 0.0f));
+    GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.traver_out, nc, -10.0f));
     e = cudaMemsetAsync(m->sc.cnt, 0, nc * sizeof(int), m->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -327,6 +362,8 @@ int gem_destroy(gem_map *m)
     if (!m) return GEM_OK;
     SetDev sd(m->dev);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    for (auto &sp : m->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+    for (cudaEvent_t e : m->free_events) cudaEventDestroy(e);
     for (void *p : m->allocs) cudaFree(p);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
@@ -364,12 +401,12 @@ static float position_to_range(float p, float shift, float resolution)
 static void clear_rows(gem_map *m, int start, int n)
 {
     const size_t cnt = (size_t)n * m->L;
-    k_clear_range<<<blocks_for(cnt, 256), 256, 0, m->stream>>>(m->ml, (size_t)start * m->L, cnt, 0);
+    GEM_LAUNCH(m, GEM_PROF_CLEAR, k_clear_range<<<blocks_for(cnt, 256), 256, 0, m->stream>>>(m->ml, (size_t)start * m->L, cnt, 0));
     m->pending.push_back(Region{1, start, n});
 }
 static void clear_cols(gem_map *m, int start, int n)
 {
-    k_clear_cols<<<blocks_for((size_t)n * m->L, 256), 256, 0, m->stream>>>(m->ml, m->L, start, n);
+    GEM_LAUNCH(m, GEM_PROF_CLEAR, k_clear_cols<<<blocks_for((size_t)n * m->L, 256), 256, 0, m->stream>>>(m->ml, m->L, start, n));
     m->pending.push_back(Region{2, start, n});
 }
 
@@ -400,7 +437,7 @@ int gem_move(gem_map *m, const float pos[3], float centre_out[2], int start_out[
             // |shift| >= L clears everything (the reference tests only the positive side,
             // gpu.cu:1033, and would write out of bounds for shift <= -L)
             if (indexShift[i] >= L || indexShift[i] <= -L) {
-                k_clear_range<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, 0, m->nc, 1);
+                GEM_LAUNCH(m, GEM_PROF_CLEAR, k_clear_range<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, 0, m->nc, 1));
                 m->pending.clear();
                 m->pending.push_back(Region{0, 0, 0});
             } else {
@@ -529,8 +566,8 @@ int gem_process_points(gem_map *m, int *map_index, const float *x, const float *
         GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
         PointInput in{};
         in.x = m->d_x; in.y = m->d_y; in.z = m->d_z;
-        k_transform_bin<IN_SOA><<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(
-            m->geom, fp, in, cn, m->sc, m->d_xt, m->d_yt, nullptr);
+        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin<IN_SOA><<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(
+            m->geom, fp, in, cn, m->sc, m->d_xt, m->d_yt, nullptr));
         AttrInput a{};
         if ((rc = run_group_fold<ATTR_NONE>(m, a, cn, false, true))) return rc; // lowest-scan only
         if (map_index) GEM_CUDA(m, cudaMemcpyAsync(map_index + off, m->sc.key, b, cudaMemcpyDeviceToHost, m->stream));
@@ -567,7 +604,7 @@ int gem_fuse(gem_map *m, int n, const int *index, const int *R, const int *G, co
             a.intensity = m->d_int;
         }
         GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
-        k_count_keys<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(m->d_keyin, cn, (int)m->nc, m->sc);
+        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_count_keys<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(m->d_keyin, cn, (int)m->nc, m->sc));
         if ((rc = run_group_fold<ATTR_INT_ARRAYS>(m, a, cn, true, false))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc;
     }
@@ -580,7 +617,7 @@ int gem_var_update(gem_map *m, float dv)
     SetDev sd(m->dev);
     // x + 0.0f == x for every non-NaN x: the GEM node always passes 0 (ElevationMapping.cpp:944-945)
     if (dv == 0.0f) return GEM_OK;
-    k_var_update<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, dv);
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_var_update<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, dv));
     if (dv < 0.0f) { // variances may drop below the floor: next Fuse must floor every cell
         m->pending.clear();
         m->pending.push_back(Region{0, 0, 0});
@@ -594,7 +631,7 @@ int gem_compute_features(gem_map *m)
     if (!m) return GEM_ERR_INVALID;
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_compute_features: tiled handles need a halo exchange (not implemented)");
     SetDev sd(m->dev);
-    k_features<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml);
+    GEM_LAUNCH(m, GEM_PROF_FEATURES, k_features<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }
@@ -602,7 +639,7 @@ int gem_compute_features(gem_map *m)
 static int copy_layer_out(gem_map *m, int layer, void *host, int slot)
 {
     float *dst = m->d_out + (size_t)slot * m->nc;
-    k_unpack_layer<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, layer, dst);
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_unpack_layer<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, layer, dst));
     GEM_CUDA(m, cudaGetLastError());
     GEM_CUDA(m, cudaMemcpyAsync(host, dst, m->nc * 4, cudaMemcpyDeviceToHost, m->stream));
     return GEM_OK;
@@ -629,8 +666,8 @@ int gem_raytracing(gem_map *m)
     if (!m) return GEM_ERR_INVALID;
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_raytracing: tiled handles need replicated lowest (not implemented)");
     SetDev sd(m->dev);
-    k_raytrace<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, m->sensorZ, m->cfg.obstacle_threshold);
-    k_fill<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml.lowest, m->nc, 10.0f); // G_Clear_maplowest
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_raytrace<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, m->sensorZ, m->cfg.obstacle_threshold));
+    GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml.lowest, m->nc, 10.0f)); // G_Clear_maplowest
     GEM_CUDA(m, cudaGetLastError());
     GEM_CUDA(m, cudaStreamSynchronize(m->stream)); // gpu.cu:1312
     return GEM_OK;
@@ -648,7 +685,7 @@ int gem_opt_move(gem_map *m, const float opt_p[2], float height_update, float al
         if (aligned_out) aligned_out[i] = c[i];
     }
     m->geom.cx = c[0]; m->geom.cy = c[1];
-    k_add_height<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, height_update);
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_add_height<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, height_update));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }
@@ -665,7 +702,7 @@ int gem_closeloop(gem_map *m, const float up[2], float height_update)
         c[i] = position_to_range(c[i], aligned, m->geom.res);
     }
     m->geom.cx = c[0]; m->geom.cy = c[1];
-    k_add_height<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, height_update);
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_add_height<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, height_update));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }
@@ -678,7 +715,7 @@ int gem_export_layers(gem_map *m, float *host_layers[9])
     int rc = ensure_out_staging(m);
     if (rc) return rc;
     dim3 grid((m->L + 31) / 32, (m->L + 31) / 32);
-    k_export_colmajor<<<grid, 256, 0, m->stream>>>(m->ml, m->L, m->d_out);
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_export_colmajor<<<grid, 256, 0, m->stream>>>(m->ml, m->L, m->d_out));
     GEM_CUDA(m, cudaGetLastError());
     for (int k = 0; k < 9; k++)
         if (host_layers[k])
@@ -705,7 +742,7 @@ int gem_set_layer(gem_map *m, int layer, const void *host_in)
     int rc = ensure_out_staging(m);
     if (rc) return rc;
     GEM_CUDA(m, cudaMemcpyAsync(m->d_out, host_in, m->nc * 4, cudaMemcpyHostToDevice, m->stream));
-    k_pack_layer<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, layer, m->d_out);
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_pack_layer<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, layer, m->d_out));
     GEM_CUDA(m, cudaGetLastError());
     GEM_CUDA(m, cudaStreamSynchronize(m->stream));
     if (layer == GEM_LAYER_VARIANCE) {
@@ -739,6 +776,40 @@ int gem_get_stats(gem_map *m, gem_stats *out)
     return GEM_OK;
 }
 
+int gem_profile_enable(gem_map *m, int on)
+{
+    if (!m) return GEM_ERR_INVALID;
+    m->profiling = on != 0;
+    return GEM_OK;
+}
+
+int gem_profile_read(gem_map *m, gem_profile *out, int reset)
+{
+    if (!m || !out) return GEM_ERR_INVALID;
+    SetDev sd(m->dev);
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    for (auto &sp : m->spans) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) {
+            m->prof_ms[sp.cls] += ms;
+            m->prof_count[sp.cls]++;
+        }
+        m->free_events.push_back(sp.e0);
+        m->free_events.push_back(sp.e1);
+    }
+    m->spans.clear();
+    out->launches = m->launches;
+    for (int i = 0; i < GEM_PROF_CLASSES; i++) {
+        out->ms[i] = m->prof_ms[i];
+        out->count[i] = m->prof_count[i];
+    }
+    if (reset) {
+        m->launches = 0;
+        for (int i = 0; i < GEM_PROF_CLASSES; i++) { m->prof_ms[i] = 0.0; m->prof_count[i] = 0; }
+    }
+    return GEM_OK;
+}
+
 int gem_host_alloc(void **out, unsigned long long bytes)
 {
     if (!out) return GEM_ERR_INVALID;
@@ -760,6 +831,7 @@ int gem_route_points(gem_map *m, const void *xyzi, const void *rgba, int n, cons
     gg.tiled = 0; // routing works on global geographic indices
     const cudaError_t e = route_points(m->stream, gg, fp, (const float4 *)xyzi, (const uchar4 *)rgba, n, tiles_r,
                                        tiles_c, m->sc, m->nc, (RouteRec *)rec_out, counts_out);
+    m->launches += 3;
     if (e != cudaSuccess) return fail(m, GEM_ERR_CUDA, std::string("gem_route_points: ") + cudaGetErrorString(e));
     return GEM_OK;
 }
@@ -774,11 +846,11 @@ int gem_fuse_records(gem_map *m, const void *rec, int n)
     for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
         GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
-        k_count_records<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, (const RouteRec *)rec + off, cn, m->sc);
-        k_alloc_cells<<<blocks_for((size_t)cn, 256, 148 * 4), 256, 0, m->stream>>>(m->sc);
-        k_scatter_records<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>((const RouteRec *)rec + off, cn, m->sc);
+        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_count_records<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, (const RouteRec *)rec + off, cn, m->sc));
+        GEM_LAUNCH(m, GEM_PROF_ALLOC, k_alloc_cells<<<blocks_for((size_t)cn, 256, 148 * 4), 256, 0, m->stream>>>(m->sc));
+        GEM_LAUNCH(m, GEM_PROF_SCATTER, k_scatter_records<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>((const RouteRec *)rec + off, cn, m->sc));
         const int fb = blocks_for((size_t)cn, FOLD_WARPS, 148 * 9);
-        k_fold<<<fb, FOLD_WARPS * 32, 0, m->stream>>>(m->geom, m->ml, m->sc, 1, 1);
+        GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<fb, FOLD_WARPS * 32, 0, m->stream>>>(m->geom, m->ml, m->sc, 1, 1));
         GEM_CUDA(m, cudaGetLastError());
         if (n > m->P && (rc = read_counters(m, cn, true))) return rc;
     }

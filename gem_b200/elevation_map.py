@@ -286,6 +286,17 @@ class ElevationMap:
         return {"points_in": st.points_in, "points_binned": st.points_binned, "cells_touched": st.cells_touched,
                 "max_points_per_cell": st.max_points_per_cell}
 
+    def profile_enable(self, on: bool = True):
+        check(self._lib.gem_profile_enable(self._h, 1 if on else 0), self._h, "gem_profile_enable")
+
+    def profile_read(self, reset: bool = True) -> dict:
+        """launch count and summed per-kernel-class device milliseconds (synchronises)"""
+        pr = _lib.GemProfile()
+        check(self._lib.gem_profile_read(self._h, C.byref(pr), 1 if reset else 0), self._h, "gem_profile_read")
+        return {"launches": int(pr.launches),
+                "ms": {n: float(pr.ms[i]) for i, n in enumerate(_lib.PROF_CLASSES)},
+                "count": {n: int(pr.count[i]) for i, n in enumerate(_lib.PROF_CLASSES)}}
+
     # -- multi-GPU tiling ---------------------------------------------------------------------
     def route_points(self, xyzi, rgba, frame: GemFrame, tiles_r: int, tiles_c: int, rec_out, counts_out):
         n = int(xyzi.shape[0])

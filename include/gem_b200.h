@@ -166,6 +166,23 @@ int gem_set_layer(gem_map *m, int layer, const void *host_in);
 int gem_get_state(gem_map *m, float centre[2], int start[2], float *sensor_z);
 int gem_get_stats(gem_map *m, gem_stats *out);
 
+/* ---- launch accounting and per-kernel device timing ------------------------------------
+ * The library counts every kernel it launches.  With profiling enabled each launch is also
+ * bracketed by CUDA events on the handle's stream (costs ~2 us per launch: use a separate
+ * pass, not the timed one).  gem_profile_read synchronises the stream. */
+enum {
+    GEM_PROF_TRANSFORM_BIN = 0, GEM_PROF_ALLOC = 1, GEM_PROF_SCATTER = 2, GEM_PROF_FOLD = 3,
+    GEM_PROF_CLEAR = 4, GEM_PROF_FEATURES = 5, GEM_PROF_RAYTRACE = 6, GEM_PROF_OTHER = 7,
+    GEM_PROF_CLASSES = 8
+};
+typedef struct gem_profile {
+    long long launches;                  /* kernels launched since the last reset          */
+    double ms[GEM_PROF_CLASSES];         /* summed device time per kernel class            */
+    long long count[GEM_PROF_CLASSES];   /* timed launches per class                       */
+} gem_profile;
+int gem_profile_enable(gem_map *m, int on);
+int gem_profile_read(gem_map *m, gem_profile *out, int reset);
+
 /* pinned host memory helpers for callers that want async-capable staging */
 int gem_host_alloc(void **out, unsigned long long bytes);
 int gem_host_free(void *p);
