@@ -52,10 +52,10 @@ class GemStats(C.Structure):
 
 
 class GemProfile(C.Structure):
-    _fields_ = [("launches", C.c_longlong), ("ms", C.c_double * 8), ("count", C.c_longlong * 8)]
+    _fields_ = [("launches", C.c_longlong), ("ms", C.c_double * 9), ("count", C.c_longlong * 9)]
 
 
-PROF_CLASSES = ["transform_bin", "alloc_cells", "scatter", "fold", "clear_floor", "features", "raytrace", "other"]
+PROF_CLASSES = ["transform_bin", "alloc_cells", "scatter", "fold", "clear_floor", "features", "raytrace", "other", "add_fused"]
 
 # every symbol include/gem_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p

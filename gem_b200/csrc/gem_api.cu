@@ -25,11 +25,6 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct Region {
-    int kind; // 0 = all cells, 1 = rows [start, start+n), 2 = cols [start, start+n)
-    int start, n;
-};
-
 } // namespace
 
 struct gem_map {
@@ -44,7 +39,14 @@ struct gem_map {
     MapLayers ml{};
     Scratch sc{};
     float sensorZ = 0.0f;
-    std::vector<Region> pending; // regions whose variance still needs the gpu.cu:533 floor
+    // deferred region operations (scroll clears of Move, the every-cell variance floor of
+    // G_fuse): executed by the next add/fuse launch, or flushed before anything observes the map
+    std::vector<RegionOp> pending;
+    Counters *ctr_buf[2] = {nullptr, nullptr};
+    int ctr_cur = 0;          // which counter buffer the NEXT call uses (it is zero)
+    Counters *ctr_last = nullptr; // counters of the last finished call
+    int coop_blocks = 0;      // co-resident grid size of the fused kernel (0 = unavailable)
+    int fused_max_points = 1 << 20;
     // staging (device), lazily allocated
     void *d_xyzi = nullptr, *d_rgba = nullptr, *d_pcl = nullptr;
     float *d_x = nullptr, *d_y = nullptr, *d_z = nullptr, *d_xt = nullptr, *d_yt = nullptr;
@@ -161,39 +163,107 @@ FrameParams make_frame(const gem_frame *f)
     return p;
 }
 
-// apply the pending every-cell variance floor (gpu.cu:533-534) where it can matter
-int flush_pending_floor(gem_map *m)
+size_t region_cells(const gem_map *m, const RegionOp &r)
 {
-    for (const Region &r : m->pending) {
-        if (r.kind == 0) {
-            GEM_LAUNCH(m, GEM_PROF_CLEAR, k_floor_range<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, 0, m->nc));
-        } else if (r.kind == 1) {
-            const size_t cnt = (size_t)r.n * m->L;
-            GEM_LAUNCH(m, GEM_PROF_CLEAR, k_floor_range<<<blocks_for(cnt, 256), 256, 0, m->stream>>>(m->ml, (size_t)r.start * m->L, cnt));
-        } else {
-            GEM_LAUNCH(m, GEM_PROF_CLEAR, k_floor_cols<<<blocks_for((size_t)r.n * m->L, 256), 256, 0, m->stream>>>(m->ml, m->L, r.start, r.n));
-        }
+    if (r.kind == 0) return m->nc;
+    if (r.kind == 1) return (size_t)r.n * m->geom.cols;
+    return (size_t)r.n * m->geom.rows;
+}
+
+int launch_regions(gem_map *m, const RegionOp *ops, int count)
+{
+    for (int i = 0; i < count; i += MAX_REGION_OPS) {
+        RegionOps ro{};
+        size_t cells = 0;
+        ro.count = (count - i < MAX_REGION_OPS) ? (count - i) : MAX_REGION_OPS;
+        for (int k = 0; k < ro.count; k++) { ro.op[k] = ops[i + k]; cells += region_cells(m, ops[i + k]); }
+        GEM_LAUNCH(m, GEM_PROF_CLEAR, k_regions<<<blocks_for(cells, ADD_BLOCK), ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, ro));
     }
-    m->pending.clear();
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }
 
+// something is about to read the layers: execute deferred clears now (a clear is visible in
+// the reference as soon as Move returns); floors stay pending until the next Fuse
+int flush_for_observer(gem_map *m)
+{
+    std::vector<RegionOp> now;
+    for (RegionOp &r : m->pending)
+        if (r.clear) {
+            RegionOp c = r;
+            c.floor_ = 0;
+            now.push_back(c);
+            r.clear = 0;
+        }
+    if (now.empty()) return GEM_OK;
+    return launch_regions(m, now.data(), (int)now.size());
+}
+
+// a Fuse-type call is starting: hand the pending operations to its first kernel.  Returns the
+// number of extra blocks that kernel should carry.
+int take_region_ops(gem_map *m, RegionOps &ro, int &region_blocks)
+{
+    ro.count = 0;
+    region_blocks = 0;
+    const int np = (int)m->pending.size();
+    if (np > MAX_REGION_OPS) { // rare: many moves without an add
+        int rc = launch_regions(m, m->pending.data(), np - MAX_REGION_OPS);
+        if (rc) return rc;
+        m->pending.erase(m->pending.begin(), m->pending.end() - MAX_REGION_OPS);
+    }
+    size_t cells = 0;
+    for (const RegionOp &r : m->pending) {
+        ro.op[ro.count++] = r;
+        cells += region_cells(m, r);
+    }
+    m->pending.clear();
+    if (ro.count) region_blocks = blocks_for(cells, ADD_BLOCK * 4, 148 * 2);
+    return GEM_OK;
+}
+
+// a Fuse with nothing to fold still applies clears + floor
+int flush_all_pending(gem_map *m)
+{
+    if (m->pending.empty()) return GEM_OK;
+    int rc = launch_regions(m, m->pending.data(), (int)m->pending.size());
+    m->pending.clear();
+    return rc;
+}
+
+void pend_all_floor(gem_map *m)
+{
+    m->pending.clear();
+    m->pending.push_back(RegionOp{0, 0, 0, 0, 1});
+}
+
+Scratch cur_scratch(gem_map *m)
+{
+    Scratch sc = m->sc;
+    sc.ctr = m->ctr_buf[m->ctr_cur];
+    sc.ctr_next = m->ctr_buf[m->ctr_cur ^ 1];
+    return sc;
+}
+void call_done(gem_map *m)
+{
+    m->ctr_last = m->ctr_buf[m->ctr_cur];
+    m->ctr_cur ^= 1;
+}
+
 // K2..K4 after the binning kernel of the current chunk
 template <int ATTR>
-int run_group_fold(gem_map *m, const AttrInput &a, int n, bool do_fuse, bool do_lowest)
+int run_group_fold(gem_map *m, const Scratch &sc, const AttrInput &a, int n, bool do_fuse, bool do_lowest)
 {
-    GEM_LAUNCH(m, GEM_PROF_ALLOC, k_alloc_cells<<<blocks_for((size_t)n, 256, 148 * 4), 256, 0, m->stream>>>(m->sc));
-    GEM_LAUNCH(m, GEM_PROF_SCATTER, k_scatter<ATTR><<<blocks_for((size_t)n, 256, 1 << 30), 256, 0, m->stream>>>(a, n, m->sc));
-    const int fb = blocks_for((size_t)n, FOLD_WARPS, 148 * 9);
-    GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<fb, FOLD_WARPS * 32, 0, m->stream>>>(m->geom, m->ml, m->sc, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
+    GEM_LAUNCH(m, GEM_PROF_ALLOC, k_alloc_cells<<<blocks_for((size_t)n, ADD_BLOCK, 148 * 4), ADD_BLOCK, 0, m->stream>>>(sc));
+    GEM_LAUNCH(m, GEM_PROF_SCATTER, k_scatter<ATTR><<<blocks_for((size_t)n, ADD_BLOCK, 148 * 16), ADD_BLOCK, 0, m->stream>>>(a, n, sc));
+    GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<blocks_for((size_t)n, ADD_BLOCK, 148 * 8), ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, sc, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
     GEM_CUDA(m, cudaGetLastError());
+    call_done(m);
     return GEM_OK;
 }
 
 int read_counters(gem_map *m, long long n_in, bool accumulate)
 {
-    GEM_CUDA(m, cudaMemcpyAsync(m->h_ctr, m->sc.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+    GEM_CUDA(m, cudaMemcpyAsync(m->h_ctr, m->ctr_last, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
     GEM_CUDA(m, cudaStreamSynchronize(m->stream));
     if (!accumulate) memset(&m->stats, 0, sizeof m->stats);
     m->stats.points_in += n_in;
@@ -245,10 +315,32 @@ int ensure_out_staging(gem_map *m)
 template <int IN, int ATTR>
 int add_chunk(gem_map *m, const PointInput &in, const AttrInput &a, int n, const FrameParams &fp)
 {
-    GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
-    GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin<IN><<<blocks_for((size_t)n, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, fp, in, n, m->sc,
-                                                                                 nullptr, nullptr, nullptr));
-    return run_group_fold<ATTR>(m, a, n, true, true);
+    RegionOps ro;
+    int rb = 0;
+    int rc = take_region_ops(m, ro, rb);
+    if (rc) return rc;
+    const Scratch sc = cur_scratch(m);
+    if (m->coop_blocks > 0 && n <= m->fused_max_points) {
+        // frame-sized call: one cooperative launch, grid barriers between the phases
+        MapGeom g = m->geom;
+        MapLayers ml = m->ml;
+        FrameParams f = fp;
+        PointInput pin = in;
+        AttrInput at = a;
+        int nn = n, do_fuse = 1, do_lowest = 1;
+        Scratch s2 = sc;
+        void *args[] = {&g, &ml, &f, &pin, &at, &nn, &s2, &ro, &do_fuse, &do_lowest};
+        int blocks = blocks_for((size_t)(n > 0 ? n : 1), ADD_BLOCK, m->coop_blocks);
+        if (ro.count && blocks < m->coop_blocks) blocks = (blocks + rb < m->coop_blocks) ? blocks + rb : m->coop_blocks;
+        GEM_LAUNCH(m, GEM_PROF_FUSED,
+                   cudaLaunchCooperativeKernel((const void *)k_add_fused<IN, ATTR>, dim3(blocks), dim3(ADD_BLOCK), args, 0, m->stream));
+        GEM_CUDA(m, cudaGetLastError());
+        call_done(m);
+        return GEM_OK;
+    }
+    const int pb = blocks_for((size_t)n, ADD_BLOCK, 148 * 16);
+    GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin<IN><<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, fp, in, n, sc, ro, pb, nullptr, nullptr));
+    return run_group_fold<ATTR>(m, sc, a, n, true, true);
 }
 
 } // namespace
@@ -332,7 +424,8 @@ int gem_create(const gem_config *cfg, gem_map **out)
         (rc = dev_alloc(m, &m->ml.rough, nc)) || (rc = dev_alloc(m, &m->ml.slope, nc)) ||
         (rc = dev_alloc(m, &m->ml.traver_out, nc)) || (rc = dev_alloc(m, &m->sc.cnt, nc)) ||
         (rc = dev_alloc(m, &m->sc.cellBase, nc)) || (rc = dev_alloc(m, &m->sc.touched, P < nc ? P : nc)) ||
-        (rc = dev_alloc(m, &m->sc.ctr, 1)) || (rc = dev_alloc(m, &m->sc.key, P)) ||
+        (rc = dev_alloc(m, &m->ctr_buf[0], 2)) || (rc = dev_alloc(m, &m->sc.key, P)) ||
+        (rc = dev_alloc(m, &m->sc.tsmall, P < nc ? P : nc)) || (rc = dev_alloc(m, &m->sc.tlarge, (P < nc ? P : nc) / FOLD_SMALL_K + 1)) ||
         (rc = dev_alloc(m, &m->sc.rank, P)) || (rc = dev_alloc(m, &m->sc.h, P)) ||
         (rc = dev_alloc(m, &m->sc.hv, P)) || (rc = dev_alloc(m, &m->sc.recA, P)) ||
         (rc = dev_alloc(m, &m->sc.recI, P)))
@@ -345,14 +438,27 @@ int gem_create(const gem_config *cfg, gem_map **out)
     GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.slope, nc, 0.0f));
     GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.traver_out, nc, -10.0f));
     e = cudaMemsetAsync(m->sc.cnt, 0, nc * sizeof(int), m->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream);
+    m->ctr_buf[1] = m->ctr_buf[0] + 1;
+    m->ctr_last = m->ctr_buf[0];
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->ctr_buf[0], 0, 2 * sizeof(Counters), m->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
     if (e != cudaSuccess) {
         m->err = std::string("gem_create: init kernels failed (is the device sm_100?): ") + cudaGetErrorString(e);
         return bail(GEM_ERR_NO_DEVICE);
     }
-    m->pending.push_back(Region{0, 0, 0}); // first Fuse floors every cell
+    pend_all_floor(m); // first Fuse floors every cell (gpu.cu:533-534)
+    {   // the fused add kernel needs a co-resident grid (cooperative launch)
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_add_fused<IN_XYZI, ATTR_XYZI>, ADD_BLOCK, 0) == cudaSuccess)
+            m->coop_blocks = per_sm * prop.multiProcessorCount;
+        const char *env = getenv("GEM_B200_FUSED");
+        if (env && atoi(env) == 0) m->coop_blocks = 0;
+        const char *envn = getenv("GEM_B200_FUSED_MAX_POINTS");
+        if (envn && atoi(envn) > 0) m->fused_max_points = atoi(envn);
+        cudaGetLastError();
+    }
     *out = m;
     return GEM_OK;
 }
@@ -398,17 +504,10 @@ static float position_to_range(float p, float shift, float resolution)
     const int shift_index = d2i_host((double)roundf(shift / resolution));
     return (float)(p_index + shift_index) * resolution;
 }
-static void clear_rows(gem_map *m, int start, int n)
-{
-    const size_t cnt = (size_t)n * m->L;
-    GEM_LAUNCH(m, GEM_PROF_CLEAR, k_clear_range<<<blocks_for(cnt, 256), 256, 0, m->stream>>>(m->ml, (size_t)start * m->L, cnt, 0));
-    m->pending.push_back(Region{1, start, n});
-}
-static void clear_cols(gem_map *m, int start, int n)
-{
-    GEM_LAUNCH(m, GEM_PROF_CLEAR, k_clear_cols<<<blocks_for((size_t)n * m->L, 256), 256, 0, m->stream>>>(m->ml, m->L, start, n));
-    m->pending.push_back(Region{2, start, n});
-}
+// scroll clears are deferred: the next add/fuse launch executes them (plus the variance
+// floor that G_fuse would apply to the cleared cells), or flush_for_observer does
+static void clear_rows(gem_map *m, int start, int n) { m->pending.push_back(RegionOp{1, start, n, 1, 1}); }
+static void clear_cols(gem_map *m, int start, int n) { m->pending.push_back(RegionOp{2, start, n, 1, 1}); }
 
 int gem_move(gem_map *m, const float pos[3], float centre_out[2], int start_out[2], float shift_out[2])
 {
@@ -438,8 +537,7 @@ int gem_move(gem_map *m, const float pos[3], float centre_out[2], int start_out[
             // gpu.cu:1033, and would write out of bounds for shift <= -L)
             if (indexShift[i] >= L || indexShift[i] <= -L) {
                 GEM_LAUNCH(m, GEM_PROF_CLEAR, k_clear_range<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, 0, m->nc, 1));
-                m->pending.clear();
-                m->pending.push_back(Region{0, 0, 0});
+                pend_all_floor(m);
             } else {
                 const int sign = indexShift[i] > 0 ? 1 : -1;
                 const int startIndex = start[i] - (sign > 0 ? 1 : 0);
@@ -473,10 +571,10 @@ int gem_add_points(gem_map *m, const void *xyzi, const void *rgba, int n, const 
 {
     if (!m || !frame || n < 0 || (n > 0 && !xyzi)) return fail(m, GEM_ERR_INVALID, "gem_add_points: bad argument");
     SetDev sd(m->dev);
-    int rc = flush_pending_floor(m);
-    if (rc) return rc;
+    int rc = GEM_OK;
     const FrameParams fp = make_frame(frame);
     memset(&m->stats, 0, sizeof m->stats);
+    if (n == 0) return flush_all_pending(m);
     for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
         PointInput in{};
@@ -498,10 +596,10 @@ int gem_add_points_host(gem_map *m, const void *xyzi, const void *rgba, int n, c
     SetDev sd(m->dev);
     int rc = ensure_host_staging(m);
     if (rc) return rc;
-    if ((rc = flush_pending_floor(m))) return rc;
     const FrameParams fp = make_frame(frame);
     memset(&m->stats, 0, sizeof m->stats);
-    for (int off = 0; off < n || (n == 0 && off == 0); off += m->P) {
+    if (n == 0) { if ((rc = flush_all_pending(m))) return rc; return gem_sync(m); }
+    for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
         if (cn > 0) {
             GEM_CUDA(m, cudaMemcpyAsync(m->d_xyzi, (const float4 *)xyzi + off, (size_t)cn * 16, cudaMemcpyHostToDevice, m->stream));
@@ -516,7 +614,6 @@ int gem_add_points_host(gem_map *m, const void *xyzi, const void *rgba, int n, c
         a.rgba = in.rgba;
         if ((rc = add_chunk<IN_XYZI, ATTR_XYZI>(m, in, a, cn, fp))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc; // also the host-visible completion point
-        if (n == 0) break;
     }
     return GEM_OK;
 }
@@ -527,10 +624,10 @@ int gem_add_cloud_pcl_host(gem_map *m, const void *pts, int n, const gem_frame *
     SetDev sd(m->dev);
     int rc = ensure_pcl_staging(m);
     if (rc) return rc;
-    if ((rc = flush_pending_floor(m))) return rc;
     const FrameParams fp = make_frame(frame);
     memset(&m->stats, 0, sizeof m->stats);
-    for (int off = 0; off < n || (n == 0 && off == 0); off += m->P) {
+    if (n == 0) { if ((rc = flush_all_pending(m))) return rc; return gem_sync(m); }
+    for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
         if (cn > 0)
             GEM_CUDA(m, cudaMemcpyAsync(m->d_pcl, (const char *)pts + (size_t)off * 32, (size_t)cn * 32, cudaMemcpyHostToDevice, m->stream));
@@ -540,7 +637,6 @@ int gem_add_cloud_pcl_host(gem_map *m, const void *pts, int n, const gem_frame *
         a.pcl = in.pcl;
         if ((rc = add_chunk<IN_PCL32, ATTR_PCL32>(m, in, a, cn, fp))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc;
-        if (n == 0) break;
     }
     return GEM_OK;
 }
@@ -563,13 +659,15 @@ int gem_process_points(gem_map *m, int *map_index, const float *x, const float *
         GEM_CUDA(m, cudaMemcpyAsync(m->d_x, x + off, b, cudaMemcpyHostToDevice, m->stream));
         GEM_CUDA(m, cudaMemcpyAsync(m->d_y, y + off, b, cudaMemcpyHostToDevice, m->stream));
         GEM_CUDA(m, cudaMemcpyAsync(m->d_z, z + off, b, cudaMemcpyHostToDevice, m->stream));
-        GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
         PointInput in{};
         in.x = m->d_x; in.y = m->d_y; in.z = m->d_z;
-        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin<IN_SOA><<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(
-            m->geom, fp, in, cn, m->sc, m->d_xt, m->d_yt, nullptr));
+        const Scratch sc = cur_scratch(m);
+        RegionOps ro{}; // Process_points does not fuse: clears/floors stay pending
+        const int pb = blocks_for((size_t)cn, ADD_BLOCK, 148 * 16);
+        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin<IN_SOA><<<pb, ADD_BLOCK, 0, m->stream>>>(
+            m->geom, m->ml, fp, in, cn, sc, ro, pb, m->d_xt, m->d_yt));
         AttrInput a{};
-        if ((rc = run_group_fold<ATTR_NONE>(m, a, cn, false, true))) return rc; // lowest-scan only
+        if ((rc = run_group_fold<ATTR_NONE>(m, sc, a, cn, false, true))) return rc; // lowest-scan only
         if (map_index) GEM_CUDA(m, cudaMemcpyAsync(map_index + off, m->sc.key, b, cudaMemcpyDeviceToHost, m->stream));
         if (var) GEM_CUDA(m, cudaMemcpyAsync(var + off, m->sc.hv, b, cudaMemcpyDeviceToHost, m->stream));
         if (z_ts) GEM_CUDA(m, cudaMemcpyAsync(z_ts + off, m->sc.h, b, cudaMemcpyDeviceToHost, m->stream));
@@ -587,8 +685,8 @@ int gem_fuse(gem_map *m, int n, const int *index, const int *R, const int *G, co
     SetDev sd(m->dev);
     int rc = ensure_compat_staging(m);
     if (rc) return rc;
-    if ((rc = flush_pending_floor(m))) return rc;
     memset(&m->stats, 0, sizeof m->stats);
+    if (n == 0) { if ((rc = flush_all_pending(m))) return rc; return gem_sync(m); }
     for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
         const size_t b = (size_t)cn * 4;
@@ -603,9 +701,13 @@ int gem_fuse(gem_map *m, int n, const int *index, const int *R, const int *G, co
             GEM_CUDA(m, cudaMemcpyAsync(m->d_int, intensity + off, b, cudaMemcpyHostToDevice, m->stream));
             a.intensity = m->d_int;
         }
-        GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
-        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_count_keys<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(m->d_keyin, cn, (int)m->nc, m->sc));
-        if ((rc = run_group_fold<ATTR_INT_ARRAYS>(m, a, cn, true, false))) return rc;
+        RegionOps ro;
+        int rb = 0;
+        if ((rc = take_region_ops(m, ro, rb))) return rc;
+        const Scratch sc = cur_scratch(m);
+        const int pb = blocks_for((size_t)cn, ADD_BLOCK, 148 * 16);
+        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_count_keys<<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, m->d_keyin, cn, (int)m->nc, sc, ro, pb));
+        if ((rc = run_group_fold<ATTR_INT_ARRAYS>(m, sc, a, cn, true, false))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc;
     }
     return GEM_OK;
@@ -617,11 +719,9 @@ int gem_var_update(gem_map *m, float dv)
     SetDev sd(m->dev);
     // x + 0.0f == x for every non-NaN x: the GEM node always passes 0 (ElevationMapping.cpp:944-945)
     if (dv == 0.0f) return GEM_OK;
+    { int rcf = flush_for_observer(m); if (rcf) return rcf; }
     GEM_LAUNCH(m, GEM_PROF_OTHER, k_var_update<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, dv));
-    if (dv < 0.0f) { // variances may drop below the floor: next Fuse must floor every cell
-        m->pending.clear();
-        m->pending.push_back(Region{0, 0, 0});
-    }
+    if (dv < 0.0f) pend_all_floor(m); // variances may drop below the floor: next Fuse floors every cell
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }
@@ -631,6 +731,7 @@ int gem_compute_features(gem_map *m)
     if (!m) return GEM_ERR_INVALID;
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_compute_features: tiled handles need a halo exchange (not implemented)");
     SetDev sd(m->dev);
+    { int rcf = flush_for_observer(m); if (rcf) return rcf; }
     GEM_LAUNCH(m, GEM_PROF_FEATURES, k_features<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
@@ -638,6 +739,7 @@ int gem_compute_features(gem_map *m)
 
 static int copy_layer_out(gem_map *m, int layer, void *host, int slot)
 {
+    { int rcf = flush_for_observer(m); if (rcf) return rcf; }
     float *dst = m->d_out + (size_t)slot * m->nc;
     GEM_LAUNCH(m, GEM_PROF_OTHER, k_unpack_layer<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, layer, dst));
     GEM_CUDA(m, cudaGetLastError());
@@ -666,6 +768,7 @@ int gem_raytracing(gem_map *m)
     if (!m) return GEM_ERR_INVALID;
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_raytracing: tiled handles need replicated lowest (not implemented)");
     SetDev sd(m->dev);
+    { int rcf = flush_for_observer(m); if (rcf) return rcf; }
     GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_raytrace<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, m->sensorZ, m->cfg.obstacle_threshold));
     GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml.lowest, m->nc, 10.0f)); // G_Clear_maplowest
     GEM_CUDA(m, cudaGetLastError());
@@ -685,6 +788,7 @@ int gem_opt_move(gem_map *m, const float opt_p[2], float height_update, float al
         if (aligned_out) aligned_out[i] = c[i];
     }
     m->geom.cx = c[0]; m->geom.cy = c[1];
+    { int rcf = flush_for_observer(m); if (rcf) return rcf; }
     GEM_LAUNCH(m, GEM_PROF_OTHER, k_add_height<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, height_update));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
@@ -702,6 +806,7 @@ int gem_closeloop(gem_map *m, const float up[2], float height_update)
         c[i] = position_to_range(c[i], aligned, m->geom.res);
     }
     m->geom.cx = c[0]; m->geom.cy = c[1];
+    { int rcf = flush_for_observer(m); if (rcf) return rcf; }
     GEM_LAUNCH(m, GEM_PROF_OTHER, k_add_height<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, height_update));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
@@ -714,6 +819,7 @@ int gem_export_layers(gem_map *m, float *host_layers[9])
     SetDev sd(m->dev);
     int rc = ensure_out_staging(m);
     if (rc) return rc;
+    if ((rc = flush_for_observer(m))) return rc;
     dim3 grid((m->L + 31) / 32, (m->L + 31) / 32);
     GEM_LAUNCH(m, GEM_PROF_OTHER, k_export_colmajor<<<grid, 256, 0, m->stream>>>(m->ml, m->L, m->d_out));
     GEM_CUDA(m, cudaGetLastError());
@@ -741,14 +847,12 @@ int gem_set_layer(gem_map *m, int layer, const void *host_in)
     SetDev sd(m->dev);
     int rc = ensure_out_staging(m);
     if (rc) return rc;
+    if ((rc = flush_for_observer(m))) return rc;
     GEM_CUDA(m, cudaMemcpyAsync(m->d_out, host_in, m->nc * 4, cudaMemcpyHostToDevice, m->stream));
     GEM_LAUNCH(m, GEM_PROF_OTHER, k_pack_layer<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, layer, m->d_out));
     GEM_CUDA(m, cudaGetLastError());
     GEM_CUDA(m, cudaStreamSynchronize(m->stream));
-    if (layer == GEM_LAYER_VARIANCE) {
-        m->pending.clear();
-        m->pending.push_back(Region{0, 0, 0});
-    }
+    if (layer == GEM_LAYER_VARIANCE) pend_all_floor(m);
     return GEM_OK;
 }
 
@@ -830,7 +934,7 @@ int gem_route_points(gem_map *m, const void *xyzi, const void *rgba, int n, cons
     MapGeom gg = m->geom;
     gg.tiled = 0; // routing works on global geographic indices
     const cudaError_t e = route_points(m->stream, gg, fp, (const float4 *)xyzi, (const uchar4 *)rgba, n, tiles_r,
-                                       tiles_c, m->sc, m->nc, (RouteRec *)rec_out, counts_out);
+                                       tiles_c, cur_scratch(m), m->nc, (RouteRec *)rec_out, counts_out);
     m->launches += 3;
     if (e != cudaSuccess) return fail(m, GEM_ERR_CUDA, std::string("gem_route_points: ") + cudaGetErrorString(e));
     return GEM_OK;
@@ -840,18 +944,18 @@ int gem_fuse_records(gem_map *m, const void *rec, int n)
 {
     if (!m || n < 0 || (n > 0 && !rec)) return fail(m, GEM_ERR_INVALID, "gem_fuse_records: bad argument");
     SetDev sd(m->dev);
-    int rc = flush_pending_floor(m);
+    int rc = flush_all_pending(m);
     if (rc) return rc;
     memset(&m->stats, 0, sizeof m->stats);
     for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
-        GEM_CUDA(m, cudaMemsetAsync(m->sc.ctr, 0, sizeof(Counters), m->stream));
-        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_count_records<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, (const RouteRec *)rec + off, cn, m->sc));
-        GEM_LAUNCH(m, GEM_PROF_ALLOC, k_alloc_cells<<<blocks_for((size_t)cn, 256, 148 * 4), 256, 0, m->stream>>>(m->sc));
-        GEM_LAUNCH(m, GEM_PROF_SCATTER, k_scatter_records<<<blocks_for((size_t)cn, 256, 1 << 30), 256, 0, m->stream>>>((const RouteRec *)rec + off, cn, m->sc));
-        const int fb = blocks_for((size_t)cn, FOLD_WARPS, 148 * 9);
-        GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<fb, FOLD_WARPS * 32, 0, m->stream>>>(m->geom, m->ml, m->sc, 1, 1));
+        const Scratch sc = cur_scratch(m);
+        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_count_records<<<blocks_for((size_t)cn, ADD_BLOCK, 1 << 30), ADD_BLOCK, 0, m->stream>>>(m->geom, (const RouteRec *)rec + off, cn, sc));
+        GEM_LAUNCH(m, GEM_PROF_ALLOC, k_alloc_cells<<<blocks_for((size_t)cn, ADD_BLOCK, 148 * 4), ADD_BLOCK, 0, m->stream>>>(sc));
+        GEM_LAUNCH(m, GEM_PROF_SCATTER, k_scatter_records<<<blocks_for((size_t)cn, ADD_BLOCK, 1 << 30), ADD_BLOCK, 0, m->stream>>>((const RouteRec *)rec + off, cn, sc));
+        GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<blocks_for((size_t)cn, ADD_BLOCK, 148 * 8), ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, sc, 1, 1));
         GEM_CUDA(m, cudaGetLastError());
+        call_done(m);
         if (n > m->P && (rc = read_counters(m, cn, true))) return rc;
     }
     if (n <= m->P) m->stats.points_in = n;

@@ -57,7 +57,6 @@ __global__ void __launch_bounds__(1024) k_route_scan(int *blockCounts, int n_own
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int total = n_owners * nblocks;
-    int owner_begin_val = 0;
     for (int base = 0; base < total; base += 1024) {
         const int idx = base + threadIdx.x;
         const int v = idx < total ? blockCounts[idx] : 0;
@@ -75,7 +74,6 @@ __global__ void __launch_bounds__(1024) k_route_scan(int *blockCounts, int n_own
         if (threadIdx.x == 1023) s_carry = incl;
         __syncthreads();
     }
-    (void)owner_begin_val;
     // owner totals from consecutive owner starts
     __syncthreads();
     for (int o = threadIdx.x; o < n_owners; o += blockDim.x) {
@@ -141,6 +139,7 @@ __global__ void __launch_bounds__(256) k_count_records(MapGeom g, const RouteRec
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
+    zero_next_counters(sc, i);
     int key = -1;
     bool first = false;
     if (i < n) {

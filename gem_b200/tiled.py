@@ -1,0 +1,201 @@
+"""Spatially tiled elevation map across the GPUs of one box (BASELINE configs 4/5).
+
+The reference is single-GPU.  When the map outgrows one GPU it is cut into geographic tiles,
+one per rank (one process per GPU, torch.distributed/NCCL for the plumbing).  Per step every
+rank transforms its own sensor's cloud (k_route_count), buckets the accepted in-grid points
+stably by owning tile (k_route_scan/k_route_write, 20-byte records), exchanges the buckets with
+ONE all-to-all over NVLink, and folds what it received into its tile (gem_fuse_records).
+Received buckets are concatenated in (source rank, source order), which is the order a single
+GPU would see if the clouds were concatenated rank by rank, so the tiled map is bit-identical
+to the single-GPU map (tests/test_tiled.py).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+REC_WORDS = 5  # RouteRec = {gkey:int32, h:f32, var:f32, rgb:u32, intensity:f32}
+
+
+def plan_tiles(world: int):
+    """(tiles_r, tiles_c): 1->1x1, 2->1x2, 4->2x2, 8->2x4 (c4 = 2x2 of 2048^2, c5 = 2x4 of 4096x2048)"""
+    r = 1
+    while r * r * 2 <= world:
+        r *= 2
+    if world % r:
+        raise ValueError(f"world size {world} is not a power of two")
+    return r, world // r
+
+
+def tile_of_rank(rank: int, world: int, L: int):
+    """(row0, rows, col0, cols) of the geographic tile a rank owns"""
+    tr, tc = plan_tiles(world)
+    th, tw = (L + tr - 1) // tr, (L + tc - 1) // tc
+    i, j = rank // tc, rank % tc
+    return i * th, min(th, L - i * th), j * tw, min(tw, L - j * tw)
+
+
+def owner_of(gx, gy, world: int, L: int):
+    tr, tc = plan_tiles(world)
+    th, tw = (L + tr - 1) // tr, (L + tc - 1) // tc
+    return (np.asarray(gx) // th) * tc + np.asarray(gy) // tw
+
+
+def exchange(send_rec, send_counts, group=None):
+    """all-to-all of variable-size record buckets.
+
+    send_rec: (n_send, REC_WORDS) int32 tensor whose rows are grouped by destination rank in
+    rank order; send_counts: python list / 1-D tensor of per-destination row counts.
+    Returns (recv_rec, recv_counts) with rows grouped by SOURCE rank in rank order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sc = torch.as_tensor(send_counts, dtype=torch.int64, device=send_rec.device).clone()
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    in_splits = [int(v) for v in sc.tolist()]
+    out_splits = [int(v) for v in rc.tolist()]
+    recv = torch.empty((sum(out_splits), REC_WORDS), dtype=send_rec.dtype, device=send_rec.device)
+    dist.all_to_all_single(recv, send_rec[: sum(in_splits)].contiguous(), output_split_sizes=out_splits,
+                           input_split_sizes=in_splits, group=group)
+    return recv, out_splits
+
+
+class TiledElevationMap:
+    """One rank's share of a global, non-scrolling L x L map."""
+
+    def __init__(self, length: int, resolution: float, max_points: int = 1 << 20, compat_box_filter: bool = False):
+        import torch
+        import torch.distributed as dist
+        from .elevation_map import ElevationMap
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.L = length
+        self.tiles_r, self.tiles_c = plan_tiles(self.world)
+        self.tile = tile_of_rank(self.rank, self.world, length)
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.current_stream()
+        self.map = ElevationMap(length, resolution, compat_box_filter=compat_box_filter, max_points=max_points,
+                                stream=self.stream.cuda_stream, tile=self.tile)
+        self.send = torch.empty((max_points, REC_WORDS), dtype=torch.int32, device=self.dev)
+        self.counts = torch.zeros(self.world, dtype=torch.int32, device=self.dev)
+        self.last_recv = 0
+
+    def add(self, xyzi, rgba, frame):
+        """route this rank's cloud, exchange, fold the received records into the own tile"""
+        self.map.route_points(xyzi, rgba, frame, self.tiles_r, self.tiles_c, self.send, self.counts)
+        counts = self.counts.cpu().tolist()  # D2H + sync: split sizes are needed on the host
+        recv, out_splits = exchange(self.send, counts)
+        self.last_recv = int(recv.shape[0])
+        if self.last_recv > self.map_capacity():
+            raise RuntimeError("received more records than max_points")
+        self.map.fuse_records(recv, self.last_recv)
+        self._keep = recv  # keep the buffer alive until the stream consumed it
+        return counts, out_splits
+
+    def map_capacity(self):
+        return self.send.shape[0]
+
+    def get_layer(self, name):
+        return self.map.get_layer(name)
+
+
+# ------------------------------------------------------------------------------------------
+# multi-GPU leg of bench.py
+# ------------------------------------------------------------------------------------------
+def sensor_offset(rank: int, world: int):
+    """one sensor per rank on a 2 x 4-style rig, 50 m apart, centred on the map"""
+    tr, tc = plan_tiles(world)
+    i, j = rank // tc, rank % tc
+    return (i - (tr - 1) / 2.0) * 50.0, (j - (tc - 1) / 2.0) * 50.0
+
+
+def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, algo_bytes_per_point):
+    import json
+    import torch
+    import torch.distributed as dist
+    from . import synth
+    import gem_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, W = args.steps, args.warmup
+    L, res = 1024 * world, 0.05
+    F = int(min(max(K + W + 2, 8), args.frames))
+    # every rank drives its own sensor: same scene generator, different seeds/poses
+    frames = gen_frames(F, first=1000 * rank)
+    ox, oy = sensor_offset(rank, world)
+    half = F / 2.0
+    fobjs, pos = [], []
+    for k, fr in enumerate(frames):
+        T = fr["T"].copy()
+        T[0, 3] = ox + (k - half)        # 1 m per frame along +x, centred on the rig position
+        T[1, 3] = oy
+        fr2 = dict(fr)
+        fr2["T"] = T
+        fobjs.append(laser_frame(fr2))
+        pos.append(np.array([T[0, 3], T[1, 3], T[2, 3]]))
+    dev = torch.device("cuda", local)
+    npts = [fr["xyzi"].shape[0] for fr in frames]
+    xyzi_d = [torch.from_numpy(fr["xyzi"]).to(dev) for fr in frames]
+    rgba_d = [torch.from_numpy(fr["rgba"]).to(dev) for fr in frames]
+    tm = TiledElevationMap(L, res, max_points=1 << 21)
+    stream = torch.cuda.current_stream()
+
+    def step(s):
+        k = pingpong(s, F)
+        tm.map.move(pos[k])
+        tm.add(xyzi_d[k], rgba_d[k], fobjs[k])
+        return npts[k]
+
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    s0 = 0
+    for s in range(10 + W):
+        step(s0); s0 += 1
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    tm.map.profile_read(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pts = 0
+    e0.record(stream)
+    for s in range(K):
+        pts += step(s0 + s)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches = tm.map.profile_read(reset=True)["launches"]
+    tot = torch.tensor([float(pts), float(launches)], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if sampler else None
+    line = None
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        value = float(tot[0].item()) / (ms_total * 1e-3) / 1e6
+        algo = algo_bytes_per_point * float(tot[0].item()) / K
+        line = {
+            "metric": "Mpoints/s fused into tiled grid", "value": value, "unit": "Mpoints/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{world} HDL-64E-shaped sensors (one per GPU) into one {L}x{L}@0.05m global map "
+                                   f"tiled {tm.tiles_r}x{tm.tiles_c} across {world}xB200, NCCL all-to-all point routing "
+                                   "(configs[3]/[4] shape)",
+                       "points_per_frame_per_gpu": float(np.mean(npts)), "distinct_frames": F,
+                       "l2": f"inputs larger than L2 per GPU: {F} frames cycled", "box_filter": "off"},
+            "roofline": {"bound": "hbm", "achieved": algo / (ms_total / K * 1e-3) / 1e9 / world, "peak": peak,
+                         "unit": "GB/s", "frac": algo / (ms_total / K * 1e-3) / 1e9 / world / peak, "traffic": None,
+                         "kernel": "whole step per GPU (route + all-to-all + fold)", "peak_source": peak_src},
+            "cpu_baseline": None,
+            "e2e": None,
+            "clocks": clocks, "gpu_launches": int(tot[1].item()),
+        }
+    dist.barrier()
+    dist.destroy_process_group()
+    return line

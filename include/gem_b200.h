@@ -173,7 +173,8 @@ int gem_get_stats(gem_map *m, gem_stats *out);
 enum {
     GEM_PROF_TRANSFORM_BIN = 0, GEM_PROF_ALLOC = 1, GEM_PROF_SCATTER = 2, GEM_PROF_FOLD = 3,
     GEM_PROF_CLEAR = 4, GEM_PROF_FEATURES = 5, GEM_PROF_RAYTRACE = 6, GEM_PROF_OTHER = 7,
-    GEM_PROF_CLASSES = 8
+    GEM_PROF_FUSED = 8, /* k_add_fused: all four add phases in one cooperative launch */
+    GEM_PROF_CLASSES = 9
 };
 typedef struct gem_profile {
     long long launches;                  /* kernels launched since the last reset          */
