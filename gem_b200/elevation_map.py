@@ -162,6 +162,23 @@ class ElevationMap:
         check(self._lib.gem_move(self._h, pos, centre, start, shift), self._h, "gem_move")
         return np.array(centre[:], np.float32), np.array(start[:], np.int32), np.array(shift[:], np.float32)
 
+    def move_fast(self, pos_c):
+        """gem_move with a prebuilt (c_float*3) and no outputs: minimal host overhead per frame"""
+        rc = self._lib.gem_move(self._h, pos_c, None, None, None)
+        if rc:
+            check(rc, self._h, "gem_move")
+
+    def add_fast(self, xyzi_ptr, rgba_ptr, n: int, frame_ref):
+        """gem_add_points with raw device addresses (c_void_p) and a byref'd gem_frame"""
+        rc = self._lib.gem_add_points(self._h, xyzi_ptr, rgba_ptr, n, frame_ref)
+        if rc:
+            check(rc, self._h, "gem_add_points")
+
+    def add_host_fast(self, xyzi_ptr, rgba_ptr, n: int, frame_ref):
+        rc = self._lib.gem_add_points_host(self._h, xyzi_ptr, rgba_ptr, n, frame_ref)
+        if rc:
+            check(rc, self._h, "gem_add_points_host")
+
     # -- fused hot path: SensorProcessorBase::process + Fuse ------------------------------------
     def add(self, xyzi, rgba, frame: GemFrame, n: int | None = None):
         """ElevationMap::add of the upstream API.  xyzi: (n,4) float32 {x,y,z,intensity};
