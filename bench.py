@@ -216,8 +216,8 @@ def run_single(args):
     fobjs = [laser_frame(fr) for fr in frames]
     npts = [fr["xyzi"].shape[0] for fr in frames]
     in_bytes = sum(n * 20 for n in npts)
-    stream = torch.cuda.current_stream()
-    m = gem_b200.ElevationMap(L, res, compat_box_filter=False, stream=stream.cuda_stream)
+    m = gem_b200.ElevationMap(L, res, compat_box_filter=False)
+    stream = m.torch_stream()   # the library-owned stream: CUDA events are recorded on it
     xyzi_d = [torch.from_numpy(fr["xyzi"]).to(dev) for fr in frames]
     rgba_d = [torch.from_numpy(fr["rgba"]).to(dev) for fr in frames]
     xyzi_h = [torch.from_numpy(fr["xyzi"]).pin_memory() for fr in frames]

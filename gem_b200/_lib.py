@@ -67,6 +67,8 @@ SYMBOLS = {
     "gem_create": (C.c_int, [C.POINTER(GemConfig), C.POINTER(_P)]),
     "gem_destroy": (C.c_int, [_P]),
     "gem_sync": (C.c_int, [_P]),
+    "gem_get_stream": (C.c_void_p, [_P]),
+    "gem_debug_phase_stamps": (C.c_int, [_P, C.c_int, C.POINTER(C.c_ulonglong)]),
     "gem_move": (C.c_int, [_P, _FP, _FP, _IP, _FP]),
     "gem_add_points": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),
     "gem_add_points_host": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),

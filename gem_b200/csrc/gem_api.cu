@@ -477,6 +477,26 @@ int gem_destroy(gem_map *m)
     return GEM_OK;
 }
 
+void *gem_get_stream(gem_map *m) { return m ? (void *)m->stream : nullptr; }
+
+int gem_debug_phase_stamps(gem_map *m, int enable, unsigned long long out[12])
+{
+    if (!m) return GEM_ERR_INVALID;
+    SetDev sd(m->dev);
+    if (enable && !m->sc.tstamp) {
+        int rc = dev_alloc(m, &m->sc.tstamp, 16);
+        if (rc) return rc;
+        GEM_CUDA(m, cudaMemsetAsync(m->sc.tstamp, 0, 16 * 8, m->stream));
+    }
+    if (out && m->sc.tstamp) {
+        GEM_CUDA(m, cudaMemcpyAsync(out, m->sc.tstamp, 12 * 8, cudaMemcpyDeviceToHost, m->stream));
+        GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+        GEM_CUDA(m, cudaMemsetAsync(m->sc.tstamp, 0, 16 * 8, m->stream));
+        GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    }
+    return GEM_OK;
+}
+
 int gem_sync(gem_map *m)
 {
     if (!m) return GEM_ERR_INVALID;

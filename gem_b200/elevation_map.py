@@ -153,6 +153,20 @@ class ElevationMap:
     def handle(self):
         return self._h
 
+    @property
+    def cuda_stream(self) -> int:
+        """cudaStream_t (as int) that all work of this map is ordered on"""
+        return int(self._lib.gem_get_stream(self._h) or 0)
+
+    def torch_stream(self):
+        import torch
+        return torch.cuda.ExternalStream(self.cuda_stream)
+
+    def debug_phase_stamps(self, enable=True):
+        out = (C.c_ulonglong * 12)()
+        check(self._lib.gem_debug_phase_stamps(self._h, 1 if enable else 0, out), self._h, "gem_debug_phase_stamps")
+        return [int(v) for v in out]
+
     # -- Move (gpu.cu:1004) -----------------------------------------------------------------
     def move(self, position):
         pos = (C.c_float * 3)(*[float(v) for v in position])

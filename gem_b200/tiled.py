@@ -74,7 +74,9 @@ class TiledElevationMap:
         self.tiles_r, self.tiles_c = plan_tiles(self.world)
         self.tile = tile_of_rank(self.rank, self.world, length)
         self.dev = torch.device("cuda", torch.cuda.current_device())
-        self.stream = torch.cuda.current_stream()
+        # NCCL collectives are ordered on torch's current stream; use a real (non-default) one
+        # and run the map's kernels on the same stream
+        self.stream = torch.cuda.Stream()
         self.map = ElevationMap(length, resolution, compat_box_filter=compat_box_filter, max_points=max_points,
                                 stream=self.stream.cuda_stream, tile=self.tile)
         self.send = torch.empty((max_points, REC_WORDS), dtype=torch.int32, device=self.dev)

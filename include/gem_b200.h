@@ -107,6 +107,11 @@ const char *gem_last_error(const gem_map *m); /* m may be NULL: last create erro
 int gem_create(const gem_config *cfg, gem_map **out);
 int gem_destroy(gem_map *m);
 int gem_sync(gem_map *m); /* wait for the handle's stream */
+/* the cudaStream_t all work of this handle is ordered on (record your own events there) */
+void *gem_get_stream(gem_map *m);
+/* debug: per-phase %globaltimer stamps (ns) of the last fused add launch (9 phase stamps of block 0,
+ * [9] = end of the last block, [10] = last block past the third barrier) */
+int gem_debug_phase_stamps(gem_map *m, int enable, unsigned long long out[12]);
 
 /* Move (gpu.cu:1004-1083): scroll the circular buffer to follow pos[0..1], record
  * pos[2] as sensorZatLowestScan.  Outputs may be NULL. */

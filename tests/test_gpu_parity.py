@@ -101,6 +101,41 @@ def test_very_long_cell_lists_fallback_paths():
     assert g.stats()["max_points_per_cell"] >= 3000
 
 
+def test_gate_boundary_is_decided_like_the_literal_expression():
+    """the CUDA fold decides the 5-sigma gate with a squared pre-test and falls back to the
+    literal |dh|/sqrt(var) > 5 inside a narrow band: sweep heights across the boundary, ulp by ulp"""
+    L = 64
+    rng = np.random.default_rng(9)
+    ncell = L * L
+    var0 = rng.uniform(1.2e-4, 0.5, ncell).astype(np.float32)
+    e0 = rng.uniform(-1, 1, ncell).astype(np.float32)
+    g, o = both(L, 0.1, compat_box_filter=False)
+    for m in (g, o):
+        m.set_layer("elevation", e0)
+        m.set_layer("variance", var0)
+    s = np.sqrt(var0.astype(np.float64))
+    keys, hs, vs = [], [], []
+    for c in range(ncell):
+        base = np.float32(e0[c] + (5.0 * s[c]) * (1 if c & 1 else -1))
+        k = int(rng.integers(-40, 41))
+        h = base
+        for _ in range(abs(k)):
+            h = np.nextafter(h, np.float32(np.inf if k > 0 else -np.inf), dtype=np.float32)
+        keys.append(c); hs.append(h); vs.append(np.float32(rng.uniform(1e-3, 0.1)))
+    keys = np.array(keys, np.int32); hs = np.array(hs, np.float32); vs = np.array(vs, np.float32)
+    ones = np.ones(ncell, np.int32)
+    for m in (g, o):
+        m.fuse_points(keys, ones, ones, ones, ones.astype(np.float32), hs, vs)
+    assert_layers_equal(g, o, ["elevation", "variance"], what="gate boundary")
+    # extreme magnitudes take the literal path
+    big = np.array([1e20, -1e20, 3e38, 1e-30, np.inf, np.nan], np.float32)
+    kk = np.arange(6, dtype=np.int32)
+    for m in (g, o):
+        m.set_layer("variance", np.full(ncell, 1e30, np.float32))
+        m.fuse_points(kk, ones[:6], ones[:6], ones[:6], ones[:6].astype(np.float32), big, np.full(6, 1e25, np.float32))
+    assert_layers_equal(g, o, ["elevation", "variance"], what="extreme magnitudes")
+
+
 def test_compat_box_filter_and_thresholds():
     fr = synth.hdl64_frame(2, compat_axes=True)
     g, o = both(200, 0.1, compat_box_filter=True)
