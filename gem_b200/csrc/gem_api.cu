@@ -934,6 +934,24 @@ int gem_profile_read(gem_map *m, gem_profile *out, int reset)
     return GEM_OK;
 }
 
+int gem_selftest_division(gem_map *m, unsigned long long seed, unsigned long long n, unsigned long long *mismatches_out,
+                          unsigned long long *fast_out)
+{
+    if (!m || !mismatches_out) return GEM_ERR_INVALID;
+    SetDev sd(m->dev);
+    unsigned long long *d = nullptr;
+    GEM_CUDA(m, cudaMalloc((void **)&d, 16));
+    GEM_CUDA(m, cudaMemsetAsync(d, 0, 16, m->stream));
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_div_selftest<<<148 * 8, 256, 0, m->stream>>>(seed, (size_t)n, d, d + 1));
+    unsigned long long h[2] = {0, 0};
+    GEM_CUDA(m, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, m->stream));
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    cudaFree(d);
+    *mismatches_out = h[0];
+    if (fast_out) *fast_out = h[1];
+    return GEM_OK;
+}
+
 int gem_host_alloc(void **out, unsigned long long bytes)
 {
     if (!out) return GEM_ERR_INVALID;

@@ -317,6 +317,11 @@ class ElevationMap:
         return {"points_in": st.points_in, "points_binned": st.points_binned, "cells_touched": st.cells_touched,
                 "max_points_per_cell": st.max_points_per_cell}
 
+    def selftest_division(self, n: int = 1 << 26, seed: int = 1):
+        bad, fast = C.c_ulonglong(), C.c_ulonglong()
+        check(self._lib.gem_selftest_division(self._h, seed, n, C.byref(bad), C.byref(fast)), self._h, "gem_selftest_division")
+        return int(bad.value), int(fast.value)
+
     def profile_enable(self, on: bool = True):
         check(self._lib.gem_profile_enable(self._h, 1 if on else 0), self._h, "gem_profile_enable")
 

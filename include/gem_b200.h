@@ -189,6 +189,12 @@ typedef struct gem_profile {
 int gem_profile_enable(gem_map *m, int on);
 int gem_profile_read(gem_map *m, gem_profile *out, int reset);
 
+/* self-test: compares the fold's shared-reciprocal division (div2_rn) with the IEEE `/` operator
+ * on n pseudo-random operand triples; mismatches must come back 0.  fast_out = how many triples
+ * took the fast path. */
+int gem_selftest_division(gem_map *m, unsigned long long seed, unsigned long long n,
+                          unsigned long long *mismatches_out, unsigned long long *fast_out);
+
 /* pinned host memory helpers for callers that want async-capable staging */
 int gem_host_alloc(void **out, unsigned long long bytes);
 int gem_host_free(void *p);

@@ -136,6 +136,14 @@ def test_gate_boundary_is_decided_like_the_literal_expression():
     assert_layers_equal(g, o, ["elevation", "variance"], what="extreme magnitudes")
 
 
+def test_shared_reciprocal_division_is_ieee_exact():
+    """div2_rn (the fold's division) must be bit-identical to the `/` operator: 2^28 random triples"""
+    g = gem_b200.ElevationMap(64, 0.1)
+    bad, fast = g.selftest_division(n=1 << 28, seed=12345)
+    assert bad == 0
+    assert fast > (1 << 27)      # most samples really exercise the fast path
+
+
 def test_compat_box_filter_and_thresholds():
     fr = synth.hdl64_frame(2, compat_axes=True)
     g, o = both(200, 0.1, compat_box_filter=True)
