@@ -269,8 +269,8 @@ int read_counters(gem_map *m, long long n_in, bool accumulate)
     m->stats.points_in += n_in;
     m->stats.points_binned += m->h_ctr->total;
     m->stats.cells_touched += m->h_ctr->ntouched;
-    int mk = m->h_ctr->maxk;
-    if (mk < 1 && m->h_ctr->ntouched > 0) mk = 1;
+    int mk = m->h_ctr->maxk; // only lists longer than FOLD_SMALL_K are tracked exactly
+    if (mk < 1 && m->h_ctr->ntouched > 0) mk = (m->h_ctr->total > m->h_ctr->ntouched) ? FOLD_SMALL_K : 1;
     if (mk > m->stats.max_points_per_cell) m->stats.max_points_per_cell = mk;
     return GEM_OK;
 }
@@ -403,6 +403,7 @@ int gem_create(const gem_config *cfg, gem_map **out)
     m->geom.cols = tiled ? cfg->tile_cols : m->L;
     m->nc = (size_t)m->geom.rows * m->geom.cols;
     m->P = cfg->max_points > 0 ? cfg->max_points : (1 << 21);
+    if (m->P > (1 << 22)) m->P = 1 << 22; // the fold's sort key packs the point index into 22 bits
 
     int rc = GEM_OK;
     auto bail = [&](int code) {
@@ -479,7 +480,7 @@ int gem_destroy(gem_map *m)
 
 void *gem_get_stream(gem_map *m) { return m ? (void *)m->stream : nullptr; }
 
-int gem_debug_phase_stamps(gem_map *m, int enable, unsigned long long out[12])
+int gem_debug_phase_stamps(gem_map *m, int enable, unsigned long long out[16])
 {
     if (!m) return GEM_ERR_INVALID;
     SetDev sd(m->dev);
@@ -489,7 +490,7 @@ int gem_debug_phase_stamps(gem_map *m, int enable, unsigned long long out[12])
         GEM_CUDA(m, cudaMemsetAsync(m->sc.tstamp, 0, 16 * 8, m->stream));
     }
     if (out && m->sc.tstamp) {
-        GEM_CUDA(m, cudaMemcpyAsync(out, m->sc.tstamp, 12 * 8, cudaMemcpyDeviceToHost, m->stream));
+        GEM_CUDA(m, cudaMemcpyAsync(out, m->sc.tstamp, 16 * 8, cudaMemcpyDeviceToHost, m->stream));
         GEM_CUDA(m, cudaStreamSynchronize(m->stream));
         GEM_CUDA(m, cudaMemsetAsync(m->sc.tstamp, 0, 16 * 8, m->stream));
         GEM_CUDA(m, cudaStreamSynchronize(m->stream));

@@ -163,7 +163,7 @@ class ElevationMap:
         return torch.cuda.ExternalStream(self.cuda_stream)
 
     def debug_phase_stamps(self, enable=True):
-        out = (C.c_ulonglong * 12)()
+        out = (C.c_ulonglong * 16)()
         check(self._lib.gem_debug_phase_stamps(self._h, 1 if enable else 0, out), self._h, "gem_debug_phase_stamps")
         return [int(v) for v in out]
 

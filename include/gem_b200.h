@@ -90,7 +90,7 @@ typedef struct gem_stats {
     long long points_in;      /* points offered by the last add/process call              */
     long long points_binned;  /* accepted by the filters AND inside the grid              */
     long long cells_touched;  /* distinct cells updated by the last add/fuse call         */
-    int max_points_per_cell;  /* longest per-cell sequential fold in the last call        */
+    int max_points_per_cell;  /* longest per-cell list of the last call (exact above 8)       */
 } gem_stats;
 
 /* layer ids for gem_get_layer / gem_set_layer */
@@ -111,7 +111,7 @@ int gem_sync(gem_map *m); /* wait for the handle's stream */
 void *gem_get_stream(gem_map *m);
 /* debug: per-phase %globaltimer stamps (ns) of the last fused add launch (9 phase stamps of block 0,
  * [9] = end of the last block, [10] = last block past the third barrier) */
-int gem_debug_phase_stamps(gem_map *m, int enable, unsigned long long out[12]);
+int gem_debug_phase_stamps(gem_map *m, int enable, unsigned long long out[16]);
 
 /* Move (gpu.cu:1004-1083): scroll the circular buffer to follow pos[0..1], record
  * pos[2] as sensorZatLowestScan.  Outputs may be NULL. */
