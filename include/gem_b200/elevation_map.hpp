@@ -1,0 +1,163 @@
+// gem_b200/elevation_map.hpp -- C++ host facade over the C ABI (include/gem_b200.h).
+//
+// Header-only, C++14.  Mirrors the reference's map object and sensor-processor interface so
+// that a maintainer of the ROS node can swap the nine ad hoc `libgpu.so` declarations for it:
+//   - elevation_mapping::ElevationMap  (ElevationMap.hpp:46-210; upstream add()/fuse()/clean()
+//     vocabulary, which BASELINE.json uses and which GEM replaced by free CUDA functions)
+//   - SensorProcessorBase::process / GPUPointCloudprocess (SensorProcessorBase.cpp:66-211)
+//   - the free functions of gpu_process.cu: Move :1004, Process_points :1085, Fuse :1154,
+//     Mapvar_update :1146, Map_feature :1256, Raytracing :1304, Map_optmove :1215,
+//     Map_closeloop :1235.
+// All arithmetic happens in libgem_b200.so (sm_100a CUDA); errors become std::runtime_error
+// (the reference prints to stderr and continues, gpu_process.cu:987-992).
+#pragma once
+
+#include <cmath>
+#include <cstddef>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../gem_b200.h"
+
+namespace gem_b200 {
+
+// PointXYZRGBICT (PointXYZRGBICT.hpp:26-48): the 32-byte PCL record the node's clouds hold.
+struct PointXYZRGBICT {
+    float x, y, z, pad;
+    unsigned char b, g, r, a;
+    float covariance, intensity, travers;
+};
+static_assert(sizeof(PointXYZRGBICT) == 32, "PCL record layout");
+
+// sensor_processor/* parameters (config/sensor_processors/*.yaml)
+struct LaserSensorProcessor { // LaserSensorProcessor.cpp:38-47
+    float min_radius = 0.018f, beam_angle = 0.0006f, beam_constant = 0.0015f;
+    double ignore_points_above = 0.8, ignore_points_below = -5.0;
+    gem_sensor_model model() const
+    {
+        gem_sensor_model m{};
+        m.type = GEM_SENSOR_LASER;
+        m.min_radius = min_radius; m.beam_angle = beam_angle; m.beam_constant = beam_constant;
+        m.normal_factor_e = 1.0;
+        return m;
+    }
+};
+struct StructuredLightSensorProcessor { // StructuredLightSensorProcessor.cpp:36-48
+    double normal_factor_a = 0.000611, normal_factor_b = 0.003587, normal_factor_c = 0.3515;
+    double normal_factor_d = 0.0, normal_factor_e = 1.0, lateral_factor = 0.01576;
+    double ignore_points_above = std::numeric_limits<double>::infinity();
+    double ignore_points_below = -std::numeric_limits<double>::infinity();
+    gem_sensor_model model() const
+    {
+        gem_sensor_model m{};
+        m.type = GEM_SENSOR_STRUCTURED_LIGHT;
+        m.normal_factor_a = normal_factor_a; m.normal_factor_b = normal_factor_b; m.normal_factor_c = normal_factor_c;
+        m.normal_factor_d = normal_factor_d; m.normal_factor_e = normal_factor_e; m.lateral_factor = lateral_factor;
+        return m;
+    }
+};
+
+// Per-frame constants exactly as GPUPointCloudprocess / readcomputerparam derive them
+// (SensorProcessorBase.cpp:171-206, 270-290).  T: row-major 4x4 map<-sensor in double
+// (the tf lookup), cast to float like the reference does.
+template <typename Sensor>
+inline gem_frame makeFrame(const double T_map_sensor[16], const Sensor &sensor, double base_z_in_map = 0.0)
+{
+    gem_frame f;
+    std::memset(&f, 0, sizeof f);
+    for (int i = 0; i < 16; i++) f.T[i] = (float)T_map_sensor[i];
+    for (int j = 0; j < 3; j++) f.sensor_jacobian[j] = (float)T_map_sensor[8 + j]; // e_z^T * R_map<-sensor
+    f.C_SB_transpose[0] = f.C_SB_transpose[4] = f.C_SB_transpose[8] = 1.0f;
+    f.P_mul_C_BM_transpose[2] = 1.0f;
+    f.rel_lower = base_z_in_map + sensor.ignore_points_below; // SPB.cpp:183
+    f.rel_upper = base_z_in_map + sensor.ignore_points_above; // SPB.cpp:184
+    f.sensor = sensor.model();
+    return f;
+}
+
+// The 9 layers ElevationMap::show writes into visualMap_ (ElevationMap.cpp:44,97-110),
+// column-major (grid_map::Matrix == Eigen::MatrixXf), NaN = empty.
+struct Layers {
+    int length = 0;
+    std::vector<float> elevation, variance, rough, slope, traver, color_r, color_g, color_b, intensity;
+    void resize(int L)
+    {
+        length = L;
+        const size_t n = (size_t)L * L;
+        for (auto *v : {&elevation, &variance, &rough, &slope, &traver, &color_r, &color_g, &color_b, &intensity}) v->resize(n);
+    }
+};
+
+class ElevationMap {
+  public:
+    ElevationMap(int length, float resolution, float mahalanobis_threshold = 2.5f, float obstacle_threshold = 0.7f,
+                 bool compat_box_filter = true, int device = -1, int max_points = 0)
+    {
+        gem_config c;
+        std::memset(&c, 0, sizeof c);
+        c.length = length; c.resolution = resolution; c.mahalanobis_threshold = mahalanobis_threshold;
+        c.obstacle_threshold = obstacle_threshold; c.compat_box_filter = compat_box_filter ? 1 : 0;
+        c.device = device; c.max_points = max_points;
+        const int rc = gem_create(&c, &h_);
+        if (rc != GEM_OK) throw std::runtime_error(std::string("gem_create: ") + gem_last_error(nullptr));
+        length_ = length;
+    }
+    ~ElevationMap() { gem_destroy(h_); }
+    ElevationMap(const ElevationMap &) = delete;
+    ElevationMap &operator=(const ElevationMap &) = delete;
+
+    int length() const { return length_; }
+    gem_map *handle() { return h_; }
+
+    // ElevationMap::move (ElevationMap.cpp:172-177) + Move (gpu_process.cu:1004)
+    void move(const float position[3], float centre[2] = nullptr, int start_index[2] = nullptr, float shift[2] = nullptr)
+    {
+        check(gem_move(h_, position, centre, start_index, shift), "gem_move");
+    }
+    // upstream ElevationMap::add == SensorProcessorBase::process + Fuse
+    // (ElevationMapping::processpoints, ElevationMapping.cpp:254-283), host PCL records
+    void add(const PointXYZRGBICT *cloud, size_t n, const gem_frame &frame)
+    {
+        check(gem_add_cloud_pcl_host(h_, cloud, (int)n, &frame), "gem_add_cloud_pcl_host");
+    }
+    // device-resident float4 {x,y,z,intensity} + uchar4 rgba (asynchronous)
+    void addDevice(const void *xyzi_device, const void *rgba_device, size_t n, const gem_frame &frame)
+    {
+        check(gem_add_points(h_, xyzi_device, rgba_device, (int)n, &frame), "gem_add_points");
+    }
+    // RobotMotionMapUpdater::update -> Mapvar_update (RobotMotionMapUpdater.cpp:81)
+    void update(float variance_increment) { check(gem_var_update(h_, variance_increment), "gem_var_update"); }
+    // upstream ElevationMap::fuse: Map_feature + show's write-back into grid_map layers
+    void fuse(Layers &out)
+    {
+        check(gem_compute_features(h_), "gem_compute_features");
+        if (out.length != length_) out.resize(length_);
+        float *ptr[9] = {out.elevation.data(), out.variance.data(), out.rough.data(), out.slope.data(), out.traver.data(),
+                         out.color_r.data(), out.color_g.data(), out.color_b.data(), out.intensity.data()};
+        check(gem_export_layers(h_, ptr), "gem_export_layers");
+    }
+    // upstream visibilityCleanup / GEM Raytracing (gpu_process.cu:1304)
+    void clean() { check(gem_raytracing(h_), "gem_raytracing"); }
+    void optMove(const float p[2], float dz, float aligned[2]) { check(gem_opt_move(h_, p, dz, aligned), "gem_opt_move"); }
+    void closeLoop(const float p[2], float dz) { check(gem_closeloop(h_, p, dz), "gem_closeloop"); }
+    gem_stats stats()
+    {
+        gem_stats s;
+        check(gem_get_stats(h_, &s), "gem_get_stats");
+        return s;
+    }
+    void sync() { check(gem_sync(h_), "gem_sync"); }
+
+  private:
+    void check(int rc, const char *what)
+    {
+        if (rc != GEM_OK) throw std::runtime_error(std::string(what) + ": " + gem_last_error(h_));
+    }
+    gem_map *h_ = nullptr;
+    int length_ = 0;
+};
+
+} // namespace gem_b200
