@@ -1,9 +1,10 @@
 /*
  * gem_oracle.c -- CPU ORACLE (test infrastructure, see gem_oracle.h header comment).
  *
- * PARITY STATUS: parity unpinned by the reference's own tests (it has none); this file is
- * a restatement of /root/reference/elevation_mapping/elevation_mapping/cuda/gpu_process.cu
- * ("gpu.cu"), cross-validated as described in gem_oracle.h.
+ * PARITY STATUS: pinned against the reference's own kernels (gpu_process.cu compiled unmodified
+ * from /root/reference by oracle/build_ref.py and run on a B200; tests/test_reference_pin.py,
+ * tests/golden/gem_golden_v1.npz) -- see gem_oracle.h.  This file restates
+ * /root/reference/elevation_mapping/elevation_mapping/cuda/gpu_process.cu ("gpu.cu").
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile).  x86-64 SSE2
  * gives true IEEE binary32 for `float` expressions (FLT_EVAL_METHOD == 0).
@@ -340,8 +341,10 @@ static float sensor_variances(const orc_sensor *s, float x, float y, float z, fl
         /* StructuredLightSensorProcessor.cpp:129-139; the parameters are doubles
          * (sensorParameters_ is a map<string,double>), pow() is double */
         float d = z; /* :130 measurementDistance = pointVector.z() */
-        float devN = (float)(s->nf_a + s->nf_b * ((double)d - s->nf_c) * ((double)d - s->nf_c) +
-                             s->nf_d * pow((double)d, s->nf_e));
+        /* pow(x, 1.0) == x exactly in IEEE libms; spelled out so that the GPU path need not
+         * match a libm pow bit for bit (realsense_d435.yaml: normal_factor_e = 1) */
+        double pw = (s->nf_e == 1.0) ? (double)d : pow((double)d, s->nf_e);
+        float devN = (float)(s->nf_a + s->nf_b * ((double)d - s->nf_c) * ((double)d - s->nf_c) + s->nf_d * pw);
         float devL = (float)(s->lateral * (double)d);
         *vN = devN * devN;
         return devL * devL;

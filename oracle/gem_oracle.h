@@ -5,17 +5,24 @@
  * and bench.py's cpu_baseline / --impl reference legs may build, link, import or run it.
  * The product (gem_b200/, include/) never touches anything under oracle/.
  *
- * PARITY STATUS: "parity unpinned by the reference's own tests".  The reference
- * (ZJU-Robotics-Lab/GEM @ d7ec953) ships no tests, no golden vectors and no CPU
- * implementation of this path; its only statement of the
- * algorithm is the CUDA file elevation_mapping/elevation_mapping/cuda/gpu_process.cu
- * ("gpu.cu" below), which needs Eigen and cannot be built in this image from its own
- * sources alone.  This file restates gpu.cu op-for-op in plain C (fp32 where the
- * reference is fp32, fp64 where C++ promotion rules make it fp64, no FMA contraction),
- * and is cross-checked three ways (tests/): a literal O(C*N) twin of G_fuse vs the O(N)
- * form, an independent numpy float32 re-derivation, and -- when oracle/_ref exists -- the
- * reference's own kernels compiled from /root/reference against a stand-in Eigen header
- * and run on the GPU box (oracle/ref_harness.cu).
+ * PARITY STATUS: PINNED AGAINST THE REFERENCE ITSELF.  The reference (ZJU-Robotics-Lab/GEM
+ * @ d7ec953) ships no tests, no golden vectors and no CPU implementation of this path
+ * (SURVEY.md section 0, 4, 8c); its only statement of the algorithm is the CUDA file
+ * elevation_mapping/elevation_mapping/cuda/gpu_process.cu ("gpu.cu" below).  That file needs
+ * Eigen, which this image lacks, so oracle/build_ref.py compiles it UNMODIFIED from
+ * /root/reference against a ~120-line stand-in for the Eigen features it uses
+ * (oracle/mini_eigen) plus an extern "C" harness (oracle/ref_harness.cu) into oracle/_ref/.
+ * The oracle is checked against those reference kernels run on a B200:
+ *   - tests/test_reference_pin.py (GPU): bit-identical map_index / height / variance /
+ *     transformed x,y / fused layers / Move outputs vs the -fmad=false build; within 1e-5
+ *     relative of the build with the reference's own flags (FMA contraction);
+ *   - tests/golden/gem_golden_v1.npz: outputs of the reference itself, generated on a B200 by
+ *     tests/golden/make_golden.py; tests/test_golden.py (CPU) replays them against the oracle.
+ * Not pinned by the reference (defined here instead, each marked ORACLE DEFINITION): the racy
+ * `lowest` update of gpu.cu:434-438, the last bit of CUDA libm's trig in the feature kernel,
+ * output values the reference leaves uninitialised, Move for shifts <= -length.
+ * Further cross-checks: a literal O(C*N) twin of G_fuse vs the O(N) form, and an independent
+ * numpy float32 re-derivation (tests/test_oracle_vs_numpy.py).
  *
  * Every function cites the reference lines it follows.  Conscious definitions where
  * the reference is racy / undefined are marked "ORACLE DEFINITION".
