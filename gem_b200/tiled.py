@@ -21,7 +21,7 @@ REC_WORDS = 5  # RouteRec = {gkey:int32, h:f32, var:f32, rgb:u32, intensity:f32}
 def plan_tiles(world: int):
     """(tiles_r, tiles_c): 1->1x1, 2->1x2, 4->2x2, 8->2x4 (c4 = 2x2 of 2048^2, c5 = 2x4 of 4096x2048)"""
     r = 1
-    while r * r * 2 <= world:
+    while (2 * r) * (2 * r) <= world:
         r *= 2
     if world % r:
         raise ValueError(f"world size {world} is not a power of two")

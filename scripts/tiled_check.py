@@ -1,0 +1,63 @@
+"""torchrun worker: N ranks build a tiled map over NCCL and compare it with the untiled map that
+rank 0 computes alone on the same clouds (bit for bit)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gem_b200  # noqa: E402
+from gem_b200 import synth, tiled  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+L, res, steps = 512 * world, 0.1, 3
+scene = synth.make_scene()
+dev = torch.device("cuda", local)
+
+
+def cloud(r, s):
+    fr = synth.hdl64_frame(10 * r + s, scene=scene)
+    ox, oy = tiled.sensor_offset(r, world)
+    fr["T"] = fr["T"].copy()
+    fr["T"][:2, 3] = (ox * 0.5 + s, oy * 0.5)
+    return fr, gem_b200.make_frame(fr["T"], gem_b200.LaserSensorProcessor())
+
+
+tm = tiled.TiledElevationMap(L, res, max_points=1 << 18)
+with torch.cuda.stream(tm.stream):
+    for s in range(steps):
+        fr, f = cloud(rank, s)
+        tm.add(torch.from_numpy(fr["xyzi"]).to(dev), torch.from_numpy(fr["rgba"]).to(dev), f)
+    tm.map.sync()
+ok = True
+if rank == 0:
+    single = gem_b200.ElevationMap(L, res, compat_box_filter=False)
+    for s in range(steps):
+        for r in range(world):      # per step: source rank order
+            fr, f = cloud(r, s)
+            single.add(fr["xyzi"], fr["rgba"], f)
+    full = {n: single.get_layer(n) for n in ("elevation", "variance", "intensity", "color_r")}
+for name in ("elevation", "variance", "intensity", "color_r"):
+    mine = torch.from_numpy(tm.get_layer(name).astype(np.float32).copy()).to(dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, gathered, dst=0)
+    if rank == 0:
+        for r in range(world):
+            r0, nr, c0, nc = tiled.tile_of_rank(r, world, L)
+            a = gathered[r].cpu().numpy()
+            b = full[name][r0:r0 + nr, c0:c0 + nc].astype(np.float32)
+            if not np.array_equal(a.view(np.uint32), b.view(np.uint32)):
+                ok = False
+                print("MISMATCH", name, r, int((a != b).sum()))
+if rank == 0:
+    valid = int((full["elevation"] != -10).sum())
+    print("valid cells", valid)
+    print("TILED_CHECK_OK" if ok and valid > 10000 else "TILED_CHECK_FAILED")
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
