@@ -91,7 +91,7 @@ SYMBOLS = {
     "gem_selftest_division": (C.c_int, [_P, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "gem_host_alloc": (C.c_int, [C.POINTER(_P), C.c_ulonglong]),
     "gem_host_free": (C.c_int, [_P]),
-    "gem_route_points": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame), C.c_int, C.c_int, _P, _P]),
+    "gem_route_points": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame), C.c_int, C.c_int, _P, _P, C.c_int]),
     "gem_fuse_records": (C.c_int, [_P, _P, C.c_int]),
 }
 

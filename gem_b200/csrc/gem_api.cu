@@ -965,7 +965,7 @@ int gem_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? GEM_OK : GE
 
 // ---- multi-GPU routing -----------------------------------------------------------------------
 int gem_route_points(gem_map *m, const void *xyzi, const void *rgba, int n, const gem_frame *frame, int tiles_r,
-                     int tiles_c, void *rec_out, int *counts_out)
+                     int tiles_c, void *rec_out, int *counts_out, int bucket_stride)
 {
     if (!m || !frame || n < 0 || tiles_r < 1 || tiles_c < 1 || !rec_out || !counts_out || (n > 0 && !xyzi))
         return fail(m, GEM_ERR_INVALID, "gem_route_points: bad argument");
@@ -975,8 +975,10 @@ int gem_route_points(gem_map *m, const void *xyzi, const void *rgba, int n, cons
     const FrameParams fp = make_frame(frame);
     MapGeom gg = m->geom;
     gg.tiled = 0; // routing works on global geographic indices
+    if (bucket_stride > 0) // padded layout: unused slots must read as "no record" (gkey = -1)
+        GEM_CUDA(m, cudaMemsetAsync(rec_out, 0xff, (size_t)tiles_r * tiles_c * bucket_stride * sizeof(RouteRec), m->stream));
     const cudaError_t e = route_points(m->stream, gg, fp, (const float4 *)xyzi, (const uchar4 *)rgba, n, tiles_r,
-                                       tiles_c, cur_scratch(m), m->nc, (RouteRec *)rec_out, counts_out);
+                                       tiles_c, cur_scratch(m), m->nc, (RouteRec *)rec_out, counts_out, bucket_stride);
     m->launches += 3;
     if (e != cudaSuccess) return fail(m, GEM_ERR_CUDA, std::string("gem_route_points: ") + cudaGetErrorString(e));
     return GEM_OK;

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(1024) k_route_scan(int *blockCounts, int n_own
 // pass 3: stable in-block rank and record write
 __global__ void __launch_bounds__(ROUTE_BLOCK)
 k_route_write(const float4 *xyzi, const uchar4 *rgba, int n, int n_owners, const int *owner_in, const int *gkey_in,
-              const float *h_in, const float *hv_in, const int *blockOffsets, RouteRec *out)
+              const float *h_in, const float *hv_in, const int *blockOffsets, RouteRec *out, int bucket_stride)
 {
     __shared__ int s_wcnt[ROUTE_BLOCK / 32][ROUTE_MAX_OWNERS];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,7 +102,9 @@ k_route_write(const float4 *xyzi, const uchar4 *rgba, int n, int n_owners, const
     if (owner >= 0) {
         int before = 0;
         for (int ww = 0; ww < w; ww++) before += s_wcnt[ww][owner];
-        const int pos = blockOffsets[owner * gridDim.x + blockIdx.x] + before + rank_in_warp;
+        int pos = blockOffsets[owner * gridDim.x + blockIdx.x] + before + rank_in_warp;
+        // fixed-stride layout: bucket o starts at o*stride (padded all-to-all, no host-side split sizes)
+        if (bucket_stride > 0) pos = pos - blockOffsets[owner * gridDim.x] + owner * bucket_stride;
         RouteRec r;
         r.gkey = gkey_in[i];
         r.h = h_in[i];
@@ -121,7 +123,7 @@ k_route_write(const float4 *xyzi, const uchar4 *rgba, int n, int n_owners, const
 //   key -> owner, rank -> gkey, h/hv as usual; blockCounts lives in cellBase.
 inline cudaError_t route_points(cudaStream_t st, const MapGeom &g, const FrameParams &fp, const float4 *xyzi,
                                 const uchar4 *rgba, int n, int tiles_r, int tiles_c, const Scratch &sc,
-                                size_t cellBase_capacity, RouteRec *out, int *counts_out)
+                                size_t cellBase_capacity, RouteRec *out, int *counts_out, int bucket_stride)
 {
     const int n_owners = tiles_r * tiles_c;
     const int nblocks = n > 0 ? (n + ROUTE_BLOCK - 1) / ROUTE_BLOCK : 1;
@@ -130,7 +132,7 @@ inline cudaError_t route_points(cudaStream_t st, const MapGeom &g, const FramePa
     k_route_count<<<nblocks, ROUTE_BLOCK, 0, st>>>(g, fp, xyzi, n, tile_h, tile_w, tiles_c, n_owners, sc.key, sc.rank,
                                                   sc.h, sc.hv, sc.cellBase);
     k_route_scan<<<1, 1024, 0, st>>>(sc.cellBase, n_owners, nblocks, counts_out);
-    k_route_write<<<nblocks, ROUTE_BLOCK, 0, st>>>(xyzi, rgba, n, n_owners, sc.key, sc.rank, sc.h, sc.hv, sc.cellBase, out);
+    k_route_write<<<nblocks, ROUTE_BLOCK, 0, st>>>(xyzi, rgba, n, n_owners, sc.key, sc.rank, sc.h, sc.hv, sc.cellBase, out, bucket_stride);
     return cudaGetLastError();
 }
 

@@ -334,10 +334,11 @@ class ElevationMap:
                 "count": {n: int(pr.count[i]) for i, n in enumerate(_lib.PROF_CLASSES)}}
 
     # -- multi-GPU tiling ---------------------------------------------------------------------
-    def route_points(self, xyzi, rgba, frame: GemFrame, tiles_r: int, tiles_c: int, rec_out, counts_out):
+    def route_points(self, xyzi, rgba, frame: GemFrame, tiles_r: int, tiles_c: int, rec_out, counts_out,
+                     bucket_stride: int = 0):
         n = int(xyzi.shape[0])
         rc = self._lib.gem_route_points(self._h, _ptr(xyzi), _ptr(rgba), n, C.byref(frame), int(tiles_r), int(tiles_c),
-                                        _ptr(rec_out), _ptr(counts_out))
+                                        _ptr(rec_out), _ptr(counts_out), int(bucket_stride))
         check(rc, self._h, "gem_route_points")
 
     def fuse_records(self, rec, n: int):

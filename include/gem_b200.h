@@ -204,11 +204,14 @@ int gem_host_free(void *p);
  * routed records {key(global geographic linear index), h, var, rgba, intensity} = 20 B
  * stably bucketed by owning tile (owner = (gx / tile_rows) * tiles_per_row + gy / tile_cols)
  * into rec_out_device, and the per-owner counts into counts_out_device[n_owners].
+ * bucket_stride == 0: buckets are packed back to back (split sizes come from the counts);
+ * bucket_stride  > 0: bucket o starts at record o*bucket_stride and unused slots hold gkey = -1,
+ * so a fixed-size all-to-all needs no host-side split sizes (no stream synchronisation).
  * gem_fuse_records: fold received records (any owner order, already in global order)
  * into this handle's tile. */
 int gem_route_points(gem_map *m, const void *xyzi_device, const void *rgba_device, int n,
                      const gem_frame *frame, int tiles_r, int tiles_c, void *rec_out_device,
-                     int *counts_out_device);
+                     int *counts_out_device, int bucket_stride);
 int gem_fuse_records(gem_map *m, const void *rec_device, int n);
 
 #ifdef __cplusplus

@@ -28,12 +28,13 @@ def cloud(r, s):
     return fr, gem_b200.make_frame(fr["T"], gem_b200.LaserSensorProcessor())
 
 
-tm = tiled.TiledElevationMap(L, res, max_points=1 << 18)
-with torch.cuda.stream(tm.stream):
-    for s in range(steps):
-        fr, f = cloud(rank, s)
-        tm.add(torch.from_numpy(fr["xyzi"]).to(dev), torch.from_numpy(fr["rgba"]).to(dev), f)
-    tm.map.sync()
+padded = os.environ.get("TILED_PADDED", "1") == "1"
+tm = tiled.TiledElevationMap(L, res, max_points=1 << 20, bucket_capacity=(1 << 17) + 4096 if padded else 0)
+for s in range(steps):
+    fr, f = cloud(rank, s)
+    tm.add(torch.from_numpy(fr["xyzi"]).to(dev), torch.from_numpy(fr["rgba"]).to(dev), f)
+tm.map.sync()
+torch.cuda.synchronize()
 ok = True
 if rank == 0:
     single = gem_b200.ElevationMap(L, res, compat_box_filter=False)
