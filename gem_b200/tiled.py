@@ -85,6 +85,10 @@ class TiledElevationMap:
         self.map = ElevationMap(length, resolution, compat_box_filter=compat_box_filter, max_points=max_points,
                                 stream=self.stream.cuda_stream, tile=self.tile)
         self.cap = int(bucket_capacity)
+        if self.cap:   # the padded all-to-all needs one capacity on every rank: agree on the maximum
+            t = torch.tensor([self.cap], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            self.cap = int(t.item())
         nsend = self.world * self.cap if self.cap else max_points
         if self.cap and nsend > max_points:
             raise ValueError("world * bucket_capacity exceeds max_points")
@@ -165,8 +169,9 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
     npts = [fr["xyzi"].shape[0] for fr in frames]
     xyzi_d = [torch.from_numpy(fr["xyzi"]).to(dev) for fr in frames]
     rgba_d = [torch.from_numpy(fr["rgba"]).to(dev) for fr in frames]
-    cap = ((max(npts) + 1023) // 1024) * 1024
+    cap = ((max(npts) + 1023) // 1024) * 1024 + 8192    # the constructor agrees on the max over ranks
     tm = TiledElevationMap(L, res, max_points=max(1 << 21, world * cap), bucket_capacity=cap)
+    cap = tm.cap
     stream = tm.stream
 
     def step(s):
@@ -194,6 +199,7 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
     dist.barrier()
     torch.cuda.synchronize()
     launches = tm.map.profile_read(reset=True)["launches"]
+    last_stats = tm.map.stats()
     tot = torch.tensor([float(pts), float(launches)], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -248,6 +254,7 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
             "cpu_baseline": None,
             "e2e": e2e,
             "clocks": clocks, "gpu_launches": int(tot[1].item()),
+            "extra": {"rank0_last_step_stats": last_stats},
         }
     dist.barrier()
     dist.destroy_process_group()
