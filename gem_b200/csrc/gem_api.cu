@@ -45,6 +45,7 @@ struct gem_map {
     Counters *ctr_buf[2] = {nullptr, nullptr};
     int ctr_cur = 0;          // which counter buffer the NEXT call uses (it is zero)
     Counters *ctr_last = nullptr; // counters of the last finished call
+    bool pdl = true;          // programmatic dependent launch between the add-path kernels
     int coop_blocks = 0;      // co-resident grid size of the fused kernel (0 = unavailable)
     int fused_max_points = 1 << 20;
     // staging (device), lazily allocated
@@ -102,6 +103,23 @@ cudaEvent_t prof_event(gem_map *m)
             __VA_ARGS__;                                         \
         }                                                        \
     } while (0)
+
+// launch with programmatic stream serialization (PDL); falls back to a plain launch when disabled
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 #define GEM_CUDA(m, expr)                                                                      \
     do {                                                                                       \
@@ -253,9 +271,9 @@ void call_done(gem_map *m)
 template <int ATTR>
 int run_group_fold(gem_map *m, const Scratch &sc, const AttrInput &a, int n, bool do_fuse, bool do_lowest)
 {
-    GEM_LAUNCH(m, GEM_PROF_ALLOC, k_alloc_cells<<<blocks_for((size_t)n, ADD_BLOCK, 148 * 4), ADD_BLOCK, 0, m->stream>>>(sc));
-    GEM_LAUNCH(m, GEM_PROF_SCATTER, k_scatter<ATTR><<<blocks_for((size_t)n, ADD_BLOCK, 148 * 16), ADD_BLOCK, 0, m->stream>>>(a, n, sc));
-    GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<blocks_for((size_t)n, ADD_BLOCK, 148 * 8), ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, sc, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
+    GEM_LAUNCH(m, GEM_PROF_ALLOC, launch_pdl(m->pdl, k_alloc_cells, blocks_for((size_t)n, ADD_BLOCK, 148 * 4), ADD_BLOCK, m->stream, sc));
+    GEM_LAUNCH(m, GEM_PROF_SCATTER, launch_pdl(m->pdl, k_scatter<ATTR>, blocks_for((size_t)n, ADD_BLOCK, 148 * 16), ADD_BLOCK, m->stream, a, n, sc));
+    GEM_LAUNCH(m, GEM_PROF_FOLD, launch_pdl(m->pdl, k_fold, blocks_for((size_t)n, ADD_BLOCK, 148 * 8), ADD_BLOCK, m->stream, m->geom, m->ml, sc, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
     GEM_CUDA(m, cudaGetLastError());
     call_done(m);
     return GEM_OK;
@@ -339,7 +357,7 @@ int add_chunk(gem_map *m, const PointInput &in, const AttrInput &a, int n, const
         return GEM_OK;
     }
     const int pb = blocks_for((size_t)n, ADD_BLOCK, 148 * 16);
-    GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin<IN><<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, fp, in, n, sc, ro, pb, nullptr, nullptr));
+    GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, launch_pdl(m->pdl, k_transform_bin<IN>, pb + rb, ADD_BLOCK, m->stream, m->geom, m->ml, fp, in, n, sc, ro, pb, (float *)nullptr, (float *)nullptr));
     return run_group_fold<ATTR>(m, sc, a, n, true, true);
 }
 
@@ -459,6 +477,8 @@ int gem_create(const gem_config *cfg, gem_map **out)
         // kernel is opt-in
         const char *env = getenv("GEM_B200_FUSED");
         if (!(env && atoi(env) == 1)) m->coop_blocks = 0;
+        const char *envp = getenv("GEM_B200_PDL");
+        if (envp && atoi(envp) == 0) m->pdl = false;
         const char *envn = getenv("GEM_B200_FUSED_MAX_POINTS");
         if (envn && atoi(envn) > 0) m->fused_max_points = atoi(envn);
         cudaGetLastError();

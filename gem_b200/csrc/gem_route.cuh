@@ -139,6 +139,8 @@ inline cudaError_t route_points(cudaStream_t st, const MapGeom &g, const FramePa
 // count/scatter for received records (fold happens in k_fold)
 __global__ void __launch_bounds__(256) k_count_records(MapGeom g, const RouteRec *rec, int n, Scratch sc)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     zero_next_counters(sc, i);
@@ -168,6 +170,8 @@ __global__ void __launch_bounds__(256) k_count_records(MapGeom g, const RouteRec
 }
 __global__ void __launch_bounds__(256) k_scatter_records(const RouteRec *rec, int n, Scratch sc)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int key = sc.key[i];
