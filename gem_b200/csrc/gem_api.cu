@@ -45,7 +45,7 @@ struct gem_map {
     Counters *ctr_buf[2] = {nullptr, nullptr};
     int ctr_cur = 0;          // which counter buffer the NEXT call uses (it is zero)
     Counters *ctr_last = nullptr; // counters of the last finished call
-    bool pdl = true;          // programmatic dependent launch between the add-path kernels
+    bool pdl = false;         // programmatic dependent launch between the add-path kernels (opt-in)
     int coop_blocks = 0;      // co-resident grid size of the fused kernel (0 = unavailable)
     int fused_max_points = 1 << 20;
     // staging (device), lazily allocated
@@ -477,8 +477,10 @@ int gem_create(const gem_config *cfg, gem_map **out)
         // kernel is opt-in
         const char *env = getenv("GEM_B200_FUSED");
         if (!(env && atoi(env) == 1)) m->coop_blocks = 0;
+        // measured on B200: with PDL the frame takes 101 us instead of 32.9 us (waiting dependent
+        // CTAs occupy the SMs the predecessor's serial fold tail needs), so it is opt-in
         const char *envp = getenv("GEM_B200_PDL");
-        if (envp && atoi(envp) == 0) m->pdl = false;
+        if (envp && atoi(envp) == 1) m->pdl = true;
         const char *envn = getenv("GEM_B200_FUSED_MAX_POINTS");
         if (envn && atoi(envn) > 0) m->fused_max_points = atoi(envn);
         cudaGetLastError();
