@@ -56,6 +56,12 @@ struct gem_map {
     float *d_out = nullptr; // 9 * nc floats read-out staging
     int *d_owner_cnt = nullptr;
     Counters *h_ctr = nullptr; // pinned
+    // pipelined host ingest (gem_add_points_host_async)
+    cudaStream_t copy_stream = nullptr;
+    void *d_axyzi[2] = {nullptr, nullptr}, *d_argba[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    Counters *h_ctr_ring = nullptr; // pinned, 2 entries
+    unsigned async_calls = 0;
     gem_stats stats{};
     std::string err;
     std::vector<void *> allocs;
@@ -498,6 +504,12 @@ int gem_destroy(gem_map *m)
     for (cudaEvent_t e : m->free_events) cudaEventDestroy(e);
     for (void *p : m->allocs) cudaFree(p);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
+    if (m->h_ctr_ring) cudaFreeHost(m->h_ctr_ring);
+    for (int i = 0; i < 2; i++) {
+        if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
+        if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
+    }
+    if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); }
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return GEM_OK;
@@ -661,6 +673,47 @@ int gem_add_points_host(gem_map *m, const void *xyzi, const void *rgba, int n, c
         if ((rc = add_chunk<IN_XYZI, ATTR_XYZI>(m, in, a, cn, fp))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc; // also the host-visible completion point
     }
+    return GEM_OK;
+}
+
+int gem_add_points_host_async(gem_map *m, const void *xyzi, const void *rgba, int n, const gem_frame *frame)
+{
+    if (!m || !frame || n < 0 || (n > 0 && !xyzi)) return fail(m, GEM_ERR_INVALID, "gem_add_points_host_async: bad argument");
+    if (n > m->P) return fail(m, GEM_ERR_INVALID, "gem_add_points_host_async: n exceeds max_points (use gem_add_points_host)");
+    SetDev sd(m->dev);
+    int rc = GEM_OK;
+    if (!m->copy_stream) { // lazy set-up: copy stream, two staging sets, events, counter ring
+        GEM_CUDA(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            if ((rc = dev_alloc(m, (float4 **)&m->d_axyzi[i], (size_t)m->P))) return rc;
+            if ((rc = dev_alloc(m, (uchar4 **)&m->d_argba[i], (size_t)m->P))) return rc;
+            GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+            GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+            GEM_CUDA(m, cudaEventRecord(m->ev_done[i], m->stream));
+        }
+        GEM_CUDA(m, cudaHostAlloc((void **)&m->h_ctr_ring, 2 * sizeof(Counters), cudaHostAllocDefault));
+    }
+    if (n == 0) return flush_all_pending(m);
+    const int b = (int)(m->async_calls++ & 1u);
+    // copy stream: wait until the kernels that last read staging set b are done, then H2D
+    GEM_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->ev_done[b], 0));
+    GEM_CUDA(m, cudaMemcpyAsync(m->d_axyzi[b], xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, m->copy_stream));
+    if (rgba) GEM_CUDA(m, cudaMemcpyAsync(m->d_argba[b], rgba, (size_t)n * 4, cudaMemcpyHostToDevice, m->copy_stream));
+    GEM_CUDA(m, cudaEventRecord(m->ev_h2d[b], m->copy_stream));
+    // compute stream: wait for the copy, run the add, read the counters back, mark set b free
+    GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_h2d[b], 0));
+    const FrameParams fp = make_frame(frame);
+    PointInput in{};
+    in.xyzi = (const float4 *)m->d_axyzi[b];
+    in.rgba = rgba ? (const uchar4 *)m->d_argba[b] : nullptr;
+    AttrInput a{};
+    a.xyzi = in.xyzi;
+    a.rgba = in.rgba;
+    if ((rc = add_chunk<IN_XYZI, ATTR_XYZI>(m, in, a, n, fp))) return rc;
+    GEM_CUDA(m, cudaMemcpyAsync(&m->h_ctr_ring[b], m->ctr_last, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+    GEM_CUDA(m, cudaEventRecord(m->ev_done[b], m->stream));
+    memset(&m->stats, 0, sizeof m->stats);
+    m->stats.points_in = n; // the rest is fetched by gem_get_stats
     return GEM_OK;
 }
 

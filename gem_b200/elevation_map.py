@@ -188,6 +188,13 @@ class ElevationMap:
         if rc:
             check(rc, self._h, "gem_add_points")
 
+    def add_host_async_fast(self, xyzi_ptr, rgba_ptr, n: int, frame_ref):
+        """gem_add_points_host_async: pinned host buffers, H2D on a copy stream overlapped with the
+        previous frame's kernels, no host synchronisation"""
+        rc = self._lib.gem_add_points_host_async(self._h, xyzi_ptr, rgba_ptr, n, frame_ref)
+        if rc:
+            check(rc, self._h, "gem_add_points_host_async")
+
     def add_host_fast(self, xyzi_ptr, rgba_ptr, n: int, frame_ref):
         rc = self._lib.gem_add_points_host(self._h, xyzi_ptr, rgba_ptr, n, frame_ref)
         if rc:

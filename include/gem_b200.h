@@ -126,6 +126,13 @@ int gem_add_points(gem_map *m, const void *xyzi_device, const void *rgba_device,
                    const gem_frame *frame);
 int gem_add_points_host(gem_map *m, const void *xyzi_host, const void *rgba_host, int n,
                         const gem_frame *frame);
+/* Pipelined host ingest: like gem_add_points_host but returns without waiting.  The copy runs on
+ * a second stream into one of two staging buffers, so frame i+1's H2D overlaps frame i's kernels;
+ * the per-call counters are read back asynchronously (gem_get_stats after gem_sync).  The host
+ * buffers must be pinned (gem_host_alloc / cudaHostRegister) and stay untouched until the call
+ * after next on this handle, or gem_sync().  n must not exceed max_points. */
+int gem_add_points_host_async(gem_map *m, const void *xyzi_pinned, const void *rgba_pinned, int n,
+                              const gem_frame *frame);
 /* PCL record ingest: n x 32-byte PointXYZRGBICT {x,y,z,pad, b,g,r,a, covariance, intensity,
  * travers} (PointXYZRGBICT.hpp:26-48), host memory, e.g. cloud->points.data(). */
 int gem_add_cloud_pcl_host(gem_map *m, const void *points32_host, int n, const gem_frame *frame);

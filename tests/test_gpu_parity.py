@@ -264,6 +264,25 @@ def test_device_pointer_path_matches_host_path():
     assert g1.stats() == g2.stats()
 
 
+def test_pipelined_host_ingest_matches_sync_path():
+    import torch
+    import ctypes as C
+    scene = synth.make_scene()
+    frames = [synth.hdl64_frame(k, scene=scene) for k in range(5)]
+    g1 = gem_b200.ElevationMap(512, 0.1, compat_box_filter=False)
+    g2 = gem_b200.ElevationMap(512, 0.1, compat_box_filter=False)
+    pinned = [(torch.from_numpy(fr["xyzi"]).pin_memory(), torch.from_numpy(fr["rgba"]).pin_memory()) for fr in frames]
+    fobj = [laser_frame(fr["T"]) for fr in frames]
+    for k, fr in enumerate(frames):
+        g1.move(fr["position"]); g2.move(fr["position"])
+        g1.add(fr["xyzi"], fr["rgba"], fobj[k])
+        g2.add_host_async_fast(C.c_void_p(pinned[k][0].data_ptr()), C.c_void_p(pinned[k][1].data_ptr()),
+                               fr["xyzi"].shape[0], C.byref(fobj[k]))
+    g2.sync()
+    assert_layers_equal(g1, g2, what="pipelined host ingest")
+    assert g1.stats() == g2.stats()
+
+
 def test_pcl_record_ingest():
     fr = synth.hdl64_frame(4)
     n = fr["xyzi"].shape[0]
