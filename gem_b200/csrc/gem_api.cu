@@ -62,6 +62,10 @@ struct gem_map {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     Counters *h_ctr_ring = nullptr; // pinned, 2 entries
     unsigned async_calls = 0;
+    // gem_add_points_multi: ring of per-call FrameParams tables (pinned host + device)
+    FrameParams *h_frames = nullptr, *d_frames = nullptr;
+    cudaEvent_t ev_frames[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned multi_calls = 0;
     gem_stats stats{};
     std::string err;
     std::vector<void *> allocs;
@@ -505,6 +509,8 @@ int gem_destroy(gem_map *m)
     for (void *p : m->allocs) cudaFree(p);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     if (m->h_ctr_ring) cudaFreeHost(m->h_ctr_ring);
+    if (m->h_frames) cudaFreeHost(m->h_frames);
+    for (int i = 0; i < 4; i++) if (m->ev_frames[i]) cudaEventDestroy(m->ev_frames[i]);
     for (int i = 0; i < 2; i++) {
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
         if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
@@ -673,6 +679,50 @@ int gem_add_points_host(gem_map *m, const void *xyzi, const void *rgba, int n, c
         if ((rc = add_chunk<IN_XYZI, ATTR_XYZI>(m, in, a, cn, fp))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc; // also the host-visible completion point
     }
+    return GEM_OK;
+}
+
+int gem_add_points_multi(gem_map *m, const void *xyzi, const void *rgba, int n_segments, const int *offsets,
+                         const gem_frame *frames)
+{
+    if (!m || !xyzi || !offsets || !frames || n_segments < 1 || n_segments > MAX_SEGMENTS)
+        return fail(m, GEM_ERR_INVALID, "gem_add_points_multi: bad argument");
+    const int n = offsets[n_segments] - offsets[0];
+    if (offsets[0] != 0 || n < 0 || n > m->P) return fail(m, GEM_ERR_INVALID, "gem_add_points_multi: offsets must start at 0 and n <= max_points");
+    for (int s = 0; s < n_segments; s++)
+        if (offsets[s + 1] < offsets[s]) return fail(m, GEM_ERR_INVALID, "gem_add_points_multi: offsets not monotone");
+    SetDev sd(m->dev);
+    int rc = GEM_OK;
+    if (!m->h_frames) {
+        GEM_CUDA(m, cudaHostAlloc((void **)&m->h_frames, 4 * MAX_SEGMENTS * sizeof(FrameParams), cudaHostAllocDefault));
+        if ((rc = dev_alloc(m, &m->d_frames, (size_t)4 * MAX_SEGMENTS))) return rc;
+        for (int i = 0; i < 4; i++) GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_frames[i], cudaEventDisableTiming));
+    }
+    if (n == 0) return flush_all_pending(m);
+    const int slot = (int)(m->multi_calls++ & 3u);
+    if (m->multi_calls > 4) GEM_CUDA(m, cudaEventSynchronize(m->ev_frames[slot])); // pinned slot free again
+    FrameParams *hf = m->h_frames + (size_t)slot * MAX_SEGMENTS, *df = m->d_frames + (size_t)slot * MAX_SEGMENTS;
+    SegTable st{};
+    st.n = n_segments;
+    for (int s = 0; s <= n_segments; s++) st.off[s] = offsets[s];
+    for (int s = 0; s < n_segments; s++) hf[s] = make_frame(&frames[s]);
+    GEM_CUDA(m, cudaMemcpyAsync(df, hf, (size_t)n_segments * sizeof(FrameParams), cudaMemcpyHostToDevice, m->stream));
+    GEM_CUDA(m, cudaEventRecord(m->ev_frames[slot], m->stream));
+    RegionOps ro;
+    int rb = 0;
+    if ((rc = take_region_ops(m, ro, rb))) return rc;
+    const Scratch sc = cur_scratch(m);
+    PointInput in{};
+    in.xyzi = (const float4 *)xyzi;
+    in.rgba = (const uchar4 *)rgba;
+    AttrInput a{};
+    a.xyzi = in.xyzi;
+    a.rgba = in.rgba;
+    const int pb = blocks_for((size_t)n, ADD_BLOCK, 148 * 32);
+    GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin_multi<<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, st, df, in, n, sc, ro, pb));
+    if ((rc = run_group_fold<ATTR_XYZI>(m, sc, a, n, true, true))) return rc;
+    memset(&m->stats, 0, sizeof m->stats);
+    m->stats.points_in = n;
     return GEM_OK;
 }
 

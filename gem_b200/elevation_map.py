@@ -214,6 +214,15 @@ class ElevationMap:
             rc = self._lib.gem_add_points_host(self._h, _ptr(xyzi), _ptr(rgba), n, C.byref(frame))
             check(rc, self._h, "gem_add_points_host")
 
+    def add_multi(self, xyzi, rgba, offsets, frames):
+        """gem_add_points_multi: several device-resident clouds (own transforms) in one launch.
+        offsets: n_segments+1 ints; frames: list of GemFrame."""
+        nseg = len(frames)
+        off = (C.c_int * (nseg + 1))(*[int(v) for v in offsets])
+        fr = (GemFrame * nseg)(*frames)
+        rc = self._lib.gem_add_points_multi(self._h, _ptr(xyzi), _ptr(rgba), nseg, off, fr)
+        check(rc, self._h, "gem_add_points_multi")
+
     def add_pcl(self, points32: np.ndarray, frame: GemFrame):
         """PointXYZRGBICT records, (n, 32) uint8 or (n, 8) float32 host array."""
         n = int(points32.shape[0])

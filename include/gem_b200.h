@@ -126,6 +126,13 @@ int gem_add_points(gem_map *m, const void *xyzi_device, const void *rgba_device,
                    const gem_frame *frame);
 int gem_add_points_host(gem_map *m, const void *xyzi_host, const void *rgba_host, int n,
                         const gem_frame *frame);
+/* Several clouds in one launch (multi-sensor rigs, BASELINE config 5): the device buffers hold
+ * n_segments clouds back to back, cloud s = points [offsets[s], offsets[s+1]) with its own
+ * per-frame constants frames[s] (both host arrays, offsets has n_segments+1 entries,
+ * n_segments <= 64).  Equivalent to n_segments gem_add_points calls in order (the per-cell
+ * order is the global point index), except that `lowest` is updated once for the whole call. */
+int gem_add_points_multi(gem_map *m, const void *xyzi_device, const void *rgba_device, int n_segments,
+                         const int *offsets, const gem_frame *frames);
 /* Pipelined host ingest: like gem_add_points_host but returns without waiting.  The copy runs on
  * a second stream into one of two staging buffers, so frame i+1's H2D overlaps frame i's kernels;
  * the per-call counters are read back asynchronously (gem_get_stats after gem_sync).  The host

@@ -283,6 +283,30 @@ def test_pipelined_host_ingest_matches_sync_path():
     assert g1.stats() == g2.stats()
 
 
+def test_multi_segment_batch_equals_sequential_adds():
+    """gem_add_points_multi (8 sensors, own transforms, one launch) == 8 sequential adds"""
+    import torch
+    L, res = 1024, 0.1
+    scene = synth.make_scene()
+    frs = [synth.hdl64_frame(k, scene=scene) for k in range(8)]
+    for k, fr in enumerate(frs):
+        fr["T"] = fr["T"].copy()
+        fr["T"][:2, 3] = (-30.0 + 9.0 * k, 12.0 * ((k % 3) - 1))
+    fobj = [laser_frame(fr["T"]) for fr in frs]
+    seq = gem_b200.ElevationMap(L, res, compat_box_filter=False)
+    for fr, f in zip(frs, fobj):
+        seq.add(fr["xyzi"], fr["rgba"], f)
+    multi = gem_b200.ElevationMap(L, res, compat_box_filter=False)
+    x = torch.from_numpy(np.concatenate([fr["xyzi"] for fr in frs])).cuda()
+    c = torch.from_numpy(np.concatenate([fr["rgba"] for fr in frs])).cuda()
+    off = np.concatenate([[0], np.cumsum([fr["xyzi"].shape[0] for fr in frs])])
+    torch.cuda.synchronize()
+    multi.add_multi(x, c, off, fobj)
+    multi.sync()
+    assert_layers_equal(seq, multi, ["elevation", "variance", "intensity", "color_r", "color_g", "color_b"], what="multi")
+    assert multi.stats()["points_in"] == int(off[-1])
+
+
 def test_pcl_record_ingest():
     fr = synth.hdl64_frame(4)
     n = fr["xyzi"].shape[0]
