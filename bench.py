@@ -352,7 +352,8 @@ def run_single(args):
 
     # ---- whole frame incl. features + ray clean-up + grid_map write-back (secondary) --------------
     Kf = min(K, 20)
-    ex = {n: np.empty((L, L), np.float32, order="F") for n in gem_b200._lib.EXPORT_LAYERS}
+    ex_pin = {n: torch.empty((L, L), dtype=torch.float32).pin_memory() for n in gem_b200._lib.EXPORT_LAYERS}
+    ex = {n: ex_pin[n].numpy().T for n in ex_pin}   # column-major views of pinned host memory
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for s in range(Kf):
@@ -395,7 +396,7 @@ def run_single(args):
         "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
         "extra": {"c5_shape_one_gpu": multi, "host_enqueue_ms_per_step": (host_ms / K) if host_ms is not None else None,
                   "frame_ms_full_pipeline": frame_ms,
-                  "frame_pipeline": "move+add+var_update+features+export(9 layers D2H)+raytracing, host-synchronous",
+                  "frame_pipeline": "move+add+var_update+features+export(9 layers, 37.7 MB D2H into pinned memory)+raytracing, host-synchronous",
                   "last_frame_stats": st, "host_cores": os.cpu_count()},
     }
     return line

@@ -432,6 +432,7 @@ int gem_create(const gem_config *cfg, gem_map **out)
     m->nc = (size_t)m->geom.rows * m->geom.cols;
     m->P = cfg->max_points > 0 ? cfg->max_points : (1 << 21);
     if (m->P > (1 << 22)) m->P = 1 << 22; // the fold's sort key packs the point index into 22 bits
+    if ((size_t)m->P < m->nc / 32 + 1) m->P = (int)(m->nc / 32 + 1); // per-point scratch doubles as the ray bitmap
 
     int rc = GEM_OK;
     auto bail = [&](int code) {
@@ -918,7 +919,13 @@ int gem_raytracing(gem_map *m)
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_raytracing: tiled handles need replicated lowest (not implemented)");
     SetDev sd(m->dev);
     { int rcf = flush_for_observer(m); if (rcf) return rcf; }
-    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_raytrace<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, m->sensorZ, m->cfg.obstacle_threshold));
+    // ray list lives in cellBase (free between add calls), its length in the spare counter buffer
+    int *ray_count = &m->ctr_buf[m->ctr_cur ^ 1]->pad4[0];
+    GEM_CUDA(m, cudaMemsetAsync(ray_count, 0, sizeof(int), m->stream));
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_collect<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, m->cfg.obstacle_threshold, m->sc.cellBase, ray_count));
+    uint32_t *bitmap = (uint32_t *)m->sc.rank; // nc/32 words <= max_points (checked at create)
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_lowest_bitmap<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->ml.lowest, (int)m->nc, bitmap));
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_trace<<<148 * 8, 256, 0, m->stream>>>(m->geom, m->ml, bitmap, m->sensorZ, m->sc.cellBase, ray_count));
     GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml.lowest, m->nc, 10.0f)); // G_Clear_maplowest
     GEM_CUDA(m, cudaGetLastError());
     GEM_CUDA(m, cudaStreamSynchronize(m->stream)); // gpu.cu:1312
