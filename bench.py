@@ -177,26 +177,43 @@ def cpu_baseline(frames, nsteps: int, threads: int, L: int, res: float):
 
 # ------------------------------------------------------------------------------------------
 def run_reference(args):
-    L, res = 1024, 0.05
+    """Reference arm.  The reference has no CPU implementation of this path (and its CUDA file is
+    not a CPU program), so this times the CPU oracle -- the restatement of the reference semantics,
+    pinned against the reference's own kernels -- on the host threads, on the same workload as the
+    gem_b200 arm at this --gpus value.  For N > 1 (tiled workload: N sensors into a (1024 N)^2 map)
+    each step is a bounded sample: sensor 0's cloud of that step, i.e. 1/N of the step's points."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
+    N = max(1, args.gpus)
+    L, res = 1024 * N, 0.05
     threads = min(os.cpu_count() or 1, 64)
     F = max(2, min(args.steps + args.warmup + 3, 16))
     frames = gen_frames(F)
+    if N > 1:   # same rig geometry as gem_b200/tiled.py: sensor 0 of the rig, 1 m per step along +x
+        from gem_b200 import tiled
+        ox, oy = tiled.sensor_offset(0, N)
+        for k, fr in enumerate(frames):
+            T = fr["T"].copy()
+            T[0, 3], T[1, 3] = ox + (k - F / 2.0), oy
+            fr["T"] = T
+            fr["position"] = np.array([0.0, 0.0, T[2, 3]])   # global map: no scroll
     nsteps = max(1, args.steps)
-    # bound the run: one step = one frame, ~3-30 ms on the host
     o_val, ms, n = cpu_baseline(frames, nsteps, threads, L, res)
     ppf = float(np.mean([f["xyzi"].shape[0] for f in frames]))
+    metric = "Mpoints/s fused into 1024x1024@0.05m grid" if N == 1 else "Mpoints/s fused into tiled grid"
+    sample = (f"{n} frames of the c2 stream, oracle process_points+fuse, {threads} threads" if N == 1 else
+              f"{n} steps, sensor 0's cloud only (1/{N} of each step's points) into the same {L}x{L} map, {threads} threads")
     line = {
-        "impl": "reference", "metric": "Mpoints/s fused into 1024x1024@0.05m grid", "value": o_val,
+        "impl": "reference", "metric": metric, "value": o_val,
         "unit": "Mpoints/s", "n_gpus": args.gpus, "steps": n, "warmup": 3, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: HDL-64E-shaped synthetic 10 Hz stream into 1024x1024@0.05m map",
-                   "points_per_frame": ppf, "note": "reference ships no CPU path and gpu_process.cu cannot be built "
-                   "here (Eigen); this arm times the CPU oracle port of its semantics"},
-        "cpu_baseline": {"value": o_val, "unit": "Mpoints/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} frames of the c2 stream, process_points+fuse, {threads} threads"},
+        "config": {"workload": ("configs[1]: HDL-64E-shaped synthetic 10 Hz stream into 1024x1024@0.05m map" if N == 1 else
+                                f"{N} HDL-64E-shaped sensors into one {L}x{L}@0.05m global map (configs[3]/[4] shape)"),
+                   "points_per_frame": ppf,
+                   "note": "the reference ships no CPU path; this arm times the CPU oracle port of its semantics "
+                           "(oracle/gem_oracle.c, pinned against the reference's kernels, DESIGN.md section 6)"},
+        "cpu_baseline": {"value": o_val, "unit": "Mpoints/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": o_val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
