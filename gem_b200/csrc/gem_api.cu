@@ -1116,7 +1116,43 @@ int gem_route_points(gem_map *m, const void *xyzi, const void *rgba, int n, cons
     return GEM_OK;
 }
 
-int gem_fuse_records(gem_map *m, const void *rec, int n)
+static int fuse_records_impl(gem_map *m, const void *rec, int n, const int *src_counts, int stride);
+
+int gem_fuse_records(gem_map *m, const void *rec, int n) { return fuse_records_impl(m, rec, n, nullptr, 1); }
+
+int gem_fuse_records_counted(gem_map *m, const void *rec, const int *src_counts, int n_sources, int bucket_stride)
+{
+    if (!m || !rec || !src_counts || n_sources < 1 || bucket_stride < 1) return fail(m, GEM_ERR_INVALID, "gem_fuse_records_counted: bad argument");
+    if ((long long)n_sources * bucket_stride > m->P) return fail(m, GEM_ERR_INVALID, "gem_fuse_records_counted: n_sources*bucket_stride exceeds max_points");
+    return fuse_records_impl(m, rec, n_sources * bucket_stride, src_counts, bucket_stride);
+}
+
+int gem_route_points_peer(gem_map *m, const void *xyzi, const void *rgba, int n, const gem_frame *frame, int tiles_r, int tiles_c,
+                          const unsigned long long *peer_recv, const unsigned long long *peer_counts, int my_rank, int bucket_stride)
+{
+    const int no = tiles_r * tiles_c;
+    if (!m || !frame || n < 0 || tiles_r < 1 || tiles_c < 1 || !peer_recv || !peer_counts || (n > 0 && !xyzi) || bucket_stride < n ||
+        my_rank < 0 || my_rank >= no)
+        return fail(m, GEM_ERR_INVALID, "gem_route_points_peer: bad argument (bucket_stride must be >= n)");
+    if (n > m->P) return fail(m, GEM_ERR_INVALID, "gem_route_points_peer: n exceeds max_points");
+    if (no > ROUTE_MAX_OWNERS) return fail(m, GEM_ERR_INVALID, "gem_route_points_peer: too many tiles");
+    SetDev sd(m->dev);
+    int rc = GEM_OK;
+    if (!m->d_owner_cnt && (rc = dev_alloc(m, &m->d_owner_cnt, ROUTE_MAX_OWNERS))) return rc;
+    const FrameParams fp = make_frame(frame);
+    MapGeom gg = m->geom;
+    gg.tiled = 0;
+    PeerTable pt;
+    memset(&pt, 0, sizeof pt);
+    for (int o = 0; o < no; o++) { pt.recv[o] = peer_recv[o]; pt.counts[o] = peer_counts[o]; }
+    const cudaError_t e = route_points(m->stream, gg, fp, (const float4 *)xyzi, (const uchar4 *)rgba, n, tiles_r, tiles_c,
+                                       cur_scratch(m), m->nc, nullptr, m->d_owner_cnt, bucket_stride, &pt, my_rank);
+    m->launches += 3;
+    if (e != cudaSuccess) return fail(m, GEM_ERR_CUDA, std::string("gem_route_points_peer: ") + cudaGetErrorString(e));
+    return GEM_OK;
+}
+
+static int fuse_records_impl(gem_map *m, const void *rec, int n, const int *src_counts, int stride)
 {
     if (!m || n < 0 || (n > 0 && !rec)) return fail(m, GEM_ERR_INVALID, "gem_fuse_records: bad argument");
     SetDev sd(m->dev);
@@ -1126,7 +1162,7 @@ int gem_fuse_records(gem_map *m, const void *rec, int n)
     for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
         const Scratch sc = cur_scratch(m);
-        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_count_records<<<blocks_for((size_t)cn, ADD_BLOCK, 1 << 30), ADD_BLOCK, 0, m->stream>>>(m->geom, (const RouteRec *)rec + off, cn, sc));
+        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_count_records<<<blocks_for((size_t)cn, ADD_BLOCK, 1 << 30), ADD_BLOCK, 0, m->stream>>>(m->geom, (const RouteRec *)rec + off, cn, sc, src_counts, stride));
         GEM_LAUNCH(m, GEM_PROF_ALLOC, k_alloc_cells<<<blocks_for((size_t)cn, ADD_BLOCK, 148 * 4), ADD_BLOCK, 0, m->stream>>>(sc));
         GEM_LAUNCH(m, GEM_PROF_SCATTER, k_scatter_records<<<blocks_for((size_t)cn, ADD_BLOCK, 1 << 30), ADD_BLOCK, 0, m->stream>>>((const RouteRec *)rec + off, cn, sc));
         GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<blocks_for((size_t)cn, ADD_BLOCK, 148 * 8), ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, sc, 1, 1));

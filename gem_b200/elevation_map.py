@@ -357,5 +357,20 @@ class ElevationMap:
                                         _ptr(rec_out), _ptr(counts_out), int(bucket_stride))
         check(rc, self._h, "gem_route_points")
 
+    def route_points_peer(self, xyzi, rgba, frame: GemFrame, tiles_r: int, tiles_c: int, peer_recv, peer_counts,
+                          my_rank: int, bucket_stride: int):
+        """peer_recv / peer_counts: lists of device addresses (ints), one per rank"""
+        n = int(xyzi.shape[0])
+        no = len(peer_recv)
+        pr = (C.c_ulonglong * no)(*[int(v) for v in peer_recv])
+        pc = (C.c_ulonglong * no)(*[int(v) for v in peer_counts])
+        rc = self._lib.gem_route_points_peer(self._h, _ptr(xyzi), _ptr(rgba), n, C.byref(frame), int(tiles_r), int(tiles_c),
+                                             pr, pc, int(my_rank), int(bucket_stride))
+        check(rc, self._h, "gem_route_points_peer")
+
+    def fuse_records_counted(self, rec, src_counts, n_sources: int, bucket_stride: int):
+        rc = self._lib.gem_fuse_records_counted(self._h, _ptr(rec), _ptr(src_counts), int(n_sources), int(bucket_stride))
+        check(rc, self._h, "gem_fuse_records_counted")
+
     def fuse_records(self, rec, n: int):
         check(self._lib.gem_fuse_records(self._h, _ptr(rec), int(n)), self._h, "gem_fuse_records")

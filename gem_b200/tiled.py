@@ -12,6 +12,7 @@ to the single-GPU map (tests/test_tiled.py).
 from __future__ import annotations
 
 import os
+import sys
 
 import numpy as np
 
@@ -67,10 +68,14 @@ class TiledElevationMap:
 
     bucket_capacity > 0 selects the padded exchange: every (source, destination) bucket has that
     fixed capacity (>= the largest cloud a rank adds per step), one fixed-size all-to-all per
-    step and no host-side split sizes; 0 selects the packed exchange (counts all-to-all + D2H)."""
+    step and no host-side split sizes; 0 selects the packed exchange (counts all-to-all + D2H).
+    peer=True (needs bucket_capacity) takes NCCL off the data path altogether: the routing kernel
+    stores every record straight into the owning rank's receive buffer over NVLink (torch symmetric
+    memory supplies the peer mappings) and one signal-pad barrier per step orders route -> fold;
+    receive buffers are double-buffered by step parity."""
 
     def __init__(self, length: int, resolution: float, max_points: int = 1 << 20, compat_box_filter: bool = False,
-                 bucket_capacity: int = 0):
+                 bucket_capacity: int = 0, peer: bool = False):
         import torch
         import torch.distributed as dist
         from .elevation_map import ElevationMap
@@ -96,12 +101,39 @@ class TiledElevationMap:
         self.recv = torch.empty((nsend, REC_WORDS), dtype=torch.int32, device=self.dev) if self.cap else None
         self.counts = torch.zeros(self.world, dtype=torch.int32, device=self.dev)
         self.last_recv = 0
+        self.peer = bool(peer and self.cap)
+        self.step = 0
+        if self.peer:
+            import torch.distributed._symmetric_memory as symm_mem
+            with torch.cuda.stream(self.stream):
+                self.p_recv = symm_mem.empty((2, self.world * self.cap, REC_WORDS), dtype=torch.int32, device=self.dev)
+                self.p_cnt = symm_mem.empty((2, 64), dtype=torch.int32, device=self.dev)
+                self.p_cnt.zero_()
+                self.h_recv = symm_mem.rendezvous(self.p_recv, dist.group.WORLD.group_name)
+                self.h_cnt = symm_mem.rendezvous(self.p_cnt, dist.group.WORLD.group_name)
+                self.h_recv.barrier(channel=0)
+            self.stream.synchronize()
+            rec_bytes = self.world * self.cap * REC_WORDS * 4
+            self._peer_recv = [[int(p) + par * rec_bytes for p in self.h_recv.buffer_ptrs] for par in (0, 1)]
+            self._peer_cnt = [[int(p) + par * 64 * 4 for p in self.h_cnt.buffer_ptrs] for par in (0, 1)]
 
     def add(self, xyzi, rgba, frame):
         """route this rank's cloud, exchange, fold the received records into the own tile"""
         import torch
         import torch.distributed as dist
         with torch.cuda.stream(self.stream):   # kernels and NCCL ordered on one stream
+            if self.peer:
+                if int(xyzi.shape[0]) > self.cap:
+                    raise ValueError("cloud larger than bucket_capacity")
+                par = self.step & 1
+                self.step += 1
+                # one kernel transforms, buckets and stores into the owners' memory over NVLink
+                self.map.route_points_peer(xyzi, rgba, frame, self.tiles_r, self.tiles_c, self._peer_recv[par],
+                                           self._peer_cnt[par], self.rank, self.cap)
+                self.h_recv.barrier(channel=0)          # device-side, on this stream: all peers' stores landed
+                self.map.fuse_records_counted(self.p_recv[par], self.p_cnt[par], self.world, self.cap)
+                self.last_recv = self.world * self.cap
+                return None, None
             if self.cap:
                 if int(xyzi.shape[0]) > self.cap:
                     raise ValueError("cloud larger than bucket_capacity")
@@ -170,7 +202,17 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
     xyzi_d = [torch.from_numpy(fr["xyzi"]).to(dev) for fr in frames]
     rgba_d = [torch.from_numpy(fr["rgba"]).to(dev) for fr in frames]
     cap = ((max(npts) + 1023) // 1024) * 1024 + 8192    # the constructor agrees on the max over ranks
-    tm = TiledElevationMap(L, res, max_points=max(1 << 21, world * cap), bucket_capacity=cap)
+    mode = os.environ.get("GEM_B200_TILED_MODE", "peer")
+    tm = None
+    if mode == "peer":
+        try:
+            tm = TiledElevationMap(L, res, max_points=max(1 << 21, world * cap), bucket_capacity=cap, peer=True)
+        except Exception as e:   # symmetric memory unavailable: NCCL padded exchange
+            if rank == 0:
+                print("peer mode unavailable:", repr(e), file=sys.stderr)
+            mode = "nccl_padded"
+    if tm is None:
+        tm = TiledElevationMap(L, res, max_points=max(1 << 21, world * cap), bucket_capacity=cap)
     cap = tm.cap
     stream = tm.stream
 
@@ -246,7 +288,9 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
                                    f"tiled {tm.tiles_r}x{tm.tiles_c} across {world}xB200, NCCL all-to-all point routing "
                                    "(configs[3]/[4] shape)",
                        "points_per_frame_per_gpu": float(np.mean(npts)), "distinct_frames": F,
-                       "exchange": f"one fixed-size NCCL all-to-all per step, {cap} x 20 B records per (src,dst) pair",
+                       "exchange": ("peer-memory routing kernel: records stored directly into the owning GPU over NVLink "
+                                    "(symmetric memory), one signal-pad barrier per step" if tm.peer else
+                                    f"one fixed-size NCCL all-to-all per step, {cap} x 20 B records per (src,dst) pair"),
                        "l2": f"inputs larger than L2 per GPU: {F} frames cycled", "box_filter": "off"},
             "roofline": {"bound": "hbm", "achieved": algo / (ms_total / K * 1e-3) / 1e9 / world, "peak": peak,
                          "unit": "GB/s", "frac": algo / (ms_total / K * 1e-3) / 1e9 / world / peak, "traffic": None,

@@ -227,6 +227,20 @@ int gem_route_points(gem_map *m, const void *xyzi_device, const void *rgba_devic
                      const gem_frame *frame, int tiles_r, int tiles_c, void *rec_out_device,
                      int *counts_out_device, int bucket_stride);
 int gem_fuse_records(gem_map *m, const void *rec_device, int n);
+/* Peer-memory routing (no collective library on the data path): like gem_route_points with a bucket
+ * stride, but every record is stored directly into the OWNING rank's receive buffer through a peer
+ * mapping (NVLink/NVSwitch): rank r's records for owner o go to peer_recv[o] + r*bucket_stride, its
+ * bucket size to ((int*)peer_counts[o])[r].  peer_recv / peer_counts: n_owners device addresses
+ * valid on this handle's device (host arrays).  The caller synchronises the ranks (one barrier)
+ * before folding with gem_fuse_records_counted. */
+int gem_route_points_peer(gem_map *m, const void *xyzi_device, const void *rgba_device, int n,
+                          const gem_frame *frame, int tiles_r, int tiles_c,
+                          const unsigned long long *peer_recv, const unsigned long long *peer_counts,
+                          int my_rank, int bucket_stride);
+/* fold a receive buffer of n_sources buckets of bucket_stride slots, bucket s filled up to
+ * src_counts_device[s] */
+int gem_fuse_records_counted(gem_map *m, const void *rec_device, const int *src_counts_device, int n_sources,
+                             int bucket_stride);
 
 #ifdef __cplusplus
 }

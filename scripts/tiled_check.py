@@ -28,8 +28,9 @@ def cloud(r, s):
     return fr, gem_b200.make_frame(fr["T"], gem_b200.LaserSensorProcessor())
 
 
-padded = os.environ.get("TILED_PADDED", "1") == "1"
-tm = tiled.TiledElevationMap(L, res, max_points=1 << 20, bucket_capacity=(1 << 17) + 4096 if padded else 0)
+mode = os.environ.get("TILED_MODE", "peer")   # peer | padded | packed
+tm = tiled.TiledElevationMap(L, res, max_points=1 << 20, bucket_capacity=0 if mode == "packed" else (1 << 17) + 4096,
+                             peer=(mode == "peer"))
 for s in range(steps):
     fr, f = cloud(rank, s)
     tm.add(torch.from_numpy(fr["xyzi"]).to(dev), torch.from_numpy(fr["rgba"]).to(dev), f)

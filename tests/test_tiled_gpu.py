@@ -70,7 +70,7 @@ def test_nccl_two_ranks():
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29655", os.path.join(ROOT, "scripts", "tiled_check.py")]
-    for padded in ("1", "0"):      # fixed-stride padded exchange and packed exchange
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, TILED_PADDED=padded))
+    for mode in ("peer", "padded", "packed"):   # NVLink peer stores / padded NCCL all-to-all / packed NCCL
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, TILED_MODE=mode))
         print(r.stdout[-3000:], r.stderr[-3000:])
         assert r.returncode == 0 and "TILED_CHECK_OK" in r.stdout
