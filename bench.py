@@ -250,10 +250,15 @@ def run_single(args):
     rhptr = [C.c_void_p(t.data_ptr()) for t in rgba_h]
     fref = [C.byref(f) for f in fobjs]
 
+    stream_mode = os.environ.get("GEM_B200_BENCH_STREAM", "1") == "1"
+
     def step(s):
         k = pingpong(s, F)
         m.move_fast(pos_c[k])
-        m.add_fast(xptr[k], rptr[k], npts[k], fref[k])
+        if stream_mode:    # gem_add_points_stream: consecutive frames software-pipelined
+            m.add_stream_fast(xptr[k], rptr[k], npts[k], fref[k])
+        else:
+            m.add_fast(xptr[k], rptr[k], npts[k], fref[k])
         return npts[k]
 
     sampler = ClockSampler(0).start()
@@ -401,7 +406,9 @@ def run_single(args):
         "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: HDL-64E-shaped synthetic 10 Hz stream into 1024x1024@0.05m robot-centric map, 1xB200",
-                   "step": "gem_move + gem_add_points on one frame (device-resident float4 xyzi + uchar4 rgba)",
+                   "step": ("gem_move + gem_add_points_stream on one frame (device-resident float4 xyzi + uchar4 rgba; "
+                            "consecutive frames software-pipelined)" if stream_mode else
+                            "gem_move + gem_add_points on one frame (device-resident float4 xyzi + uchar4 rgba)"),
                    "points_per_frame": float(np.mean(npts)), "distinct_frames": F,
                    "l2": (f"inputs larger than L2: {F} distinct frames = {in_bytes/1e6:.0f} MB cycled" if flush is None
                           else "L2 flushed (256 MB write) between timed steps"),

@@ -72,6 +72,7 @@ SYMBOLS = {
     "gem_move": (C.c_int, [_P, _FP, _FP, _IP, _FP]),
     "gem_add_points": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),
     "gem_add_points_host": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),
+    "gem_add_points_stream": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),
     "gem_add_points_multi": (C.c_int, [_P, _P, _P, C.c_int, _IP, C.POINTER(GemFrame)]),
     "gem_add_points_host_async": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),
     "gem_add_cloud_pcl_host": (C.c_int, [_P, _P, C.c_int, C.POINTER(GemFrame)]),

@@ -62,6 +62,13 @@ struct gem_map {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     Counters *h_ctr_ring = nullptr; // pinned, 2 entries
     unsigned async_calls = 0;
+    // gem_add_points_stream: frame-pipelined mode (own scratch sets, front stream, events)
+    bool pipe_ready = false;
+    Scratch pipe_sc[2];
+    Counters *pipe_ctr[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t front_stream = nullptr;
+    cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_fold[2] = {nullptr, nullptr};
+    unsigned pipe_calls = 0;
     // gem_add_points_multi: ring of per-call FrameParams tables (pinned host + device)
     FrameParams *h_frames = nullptr, *d_frames = nullptr;
     cudaEvent_t ev_frames[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -100,6 +107,19 @@ cudaEvent_t prof_event(gem_map *m)
 }
 // every kernel launch of the library goes through this macro: counts the launch and, when
 // profiling is on, brackets it with CUDA events on the handle's stream
+#define GEM_LAUNCH_ON(m, st, cls, ...)                           \
+    do {                                                         \
+        (m)->launches++;                                         \
+        if ((m)->profiling) {                                    \
+            gem_map::Span sp__{(cls), prof_event(m), prof_event(m)}; \
+            cudaEventRecord(sp__.e0, (st));                      \
+            __VA_ARGS__;                                         \
+            cudaEventRecord(sp__.e1, (st));                      \
+            (m)->spans.push_back(sp__);                          \
+        } else {                                                 \
+            __VA_ARGS__;                                         \
+        }                                                        \
+    } while (0)
 #define GEM_LAUNCH(m, cls, ...)                                  \
     do {                                                         \
         (m)->launches++;                                         \
@@ -511,6 +531,11 @@ int gem_destroy(gem_map *m)
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     if (m->h_ctr_ring) cudaFreeHost(m->h_ctr_ring);
     if (m->h_frames) cudaFreeHost(m->h_frames);
+    for (int i = 0; i < 2; i++) {
+        if (m->ev_front[i]) cudaEventDestroy(m->ev_front[i]);
+        if (m->ev_fold[i]) cudaEventDestroy(m->ev_fold[i]);
+    }
+    if (m->front_stream) { cudaStreamSynchronize(m->front_stream); cudaStreamDestroy(m->front_stream); }
     for (int i = 0; i < 4; i++) if (m->ev_frames[i]) cudaEventDestroy(m->ev_frames[i]);
     for (int i = 0; i < 2; i++) {
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
@@ -680,6 +705,77 @@ int gem_add_points_host(gem_map *m, const void *xyzi, const void *rgba, int n, c
         if ((rc = add_chunk<IN_XYZI, ATTR_XYZI>(m, in, a, cn, fp))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc; // also the host-visible completion point
     }
+    return GEM_OK;
+}
+
+static int pipe_setup(gem_map *m)
+{
+    if (m->pipe_ready) return GEM_OK;
+    int rc;
+    const size_t nc = m->nc, P = (size_t)m->P, T = P < nc ? P : nc;
+    for (int i = 0; i < 2; i++) {
+        Scratch &sc = m->pipe_sc[i];
+        memset(&sc, 0, sizeof sc);
+        if ((rc = dev_alloc(m, &sc.cnt, nc)) || (rc = dev_alloc(m, &sc.cellBase, nc)) || (rc = dev_alloc(m, &sc.touched, T)) ||
+            (rc = dev_alloc(m, &sc.tsmall, T)) || (rc = dev_alloc(m, &sc.tlarge, T / FOLD_SMALL_K + 1)) ||
+            (rc = dev_alloc(m, &sc.key, P)) || (rc = dev_alloc(m, &sc.rank, P)) || (rc = dev_alloc(m, &sc.h, P)) ||
+            (rc = dev_alloc(m, &sc.hv, P)) || (rc = dev_alloc(m, &sc.recA, P)) || (rc = dev_alloc(m, &sc.recI, P)))
+            return rc;
+        GEM_CUDA(m, cudaMemsetAsync(sc.cnt, 0, nc * sizeof(int), m->stream));
+        GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_front[i], cudaEventDisableTiming));
+        GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_fold[i], cudaEventDisableTiming));
+    }
+    if ((rc = dev_alloc(m, &m->pipe_ctr[0], 3))) return rc;
+    m->pipe_ctr[1] = m->pipe_ctr[0] + 1;
+    m->pipe_ctr[2] = m->pipe_ctr[0] + 2;
+    GEM_CUDA(m, cudaMemsetAsync(m->pipe_ctr[0], 0, 3 * sizeof(Counters), m->stream));
+    GEM_CUDA(m, cudaStreamCreateWithFlags(&m->front_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) GEM_CUDA(m, cudaEventRecord(m->ev_fold[i], m->stream)); // sets are free once init is done
+    m->pipe_ready = true;
+    return GEM_OK;
+}
+
+int gem_add_points_stream(gem_map *m, const void *xyzi, const void *rgba, int n, const gem_frame *frame)
+{
+    if (!m || !frame || n < 0 || (n > 0 && !xyzi)) return fail(m, GEM_ERR_INVALID, "gem_add_points_stream: bad argument");
+    if (n > m->P) return fail(m, GEM_ERR_INVALID, "gem_add_points_stream: n exceeds max_points (use gem_add_points)");
+    SetDev sd(m->dev);
+    int rc = pipe_setup(m);
+    if (rc) return rc;
+    if (n == 0) return flush_all_pending(m);
+    const unsigned i = m->pipe_calls++;
+    const int par = (int)(i & 1u), c = (int)(i % 3u);
+    Scratch sc = m->pipe_sc[par];
+    sc.ctr = m->pipe_ctr[c];
+    sc.ctr_next = m->pipe_ctr[(c + 1) % 3];
+    sc.tstamp = nullptr;
+    const FrameParams fp = make_frame(frame);
+    PointInput in{};
+    in.xyzi = (const float4 *)xyzi;
+    in.rgba = (const uchar4 *)rgba;
+    AttrInput a{};
+    a.xyzi = in.xyzi;
+    a.rgba = in.rgba;
+    // front stream: transform+bin, alloc, scatter of THIS frame -- may overlap the fold of the previous
+    // frame; it only waits for the fold that last used this scratch set (two calls ago)
+    GEM_CUDA(m, cudaStreamWaitEvent(m->front_stream, m->ev_fold[par], 0));
+    RegionOps none{};
+    const int pb = blocks_for((size_t)n, ADD_BLOCK, 148 * 16);
+    GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_TRANSFORM_BIN,
+                  k_transform_bin<IN_XYZI><<<pb, ADD_BLOCK, 0, m->front_stream>>>(m->geom, m->ml, fp, in, n, sc, none, pb, nullptr, nullptr));
+    GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_ALLOC, k_alloc_cells<<<blocks_for((size_t)n, ADD_BLOCK, 148 * 4), ADD_BLOCK, 0, m->front_stream>>>(sc));
+    GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_SCATTER,
+                  k_scatter<ATTR_XYZI><<<blocks_for((size_t)n, ADD_BLOCK, 148 * 16), ADD_BLOCK, 0, m->front_stream>>>(a, n, sc));
+    GEM_CUDA(m, cudaEventRecord(m->ev_front[par], m->front_stream));
+    // main stream: deferred scroll clears / floors, then the fold (the only kernel that touches the layers)
+    if (!m->pending.empty() && (rc = flush_all_pending(m))) return rc;
+    GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_front[par], 0));
+    GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<blocks_for((size_t)n, ADD_BLOCK, 148 * 8), ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, sc, 1, 1));
+    GEM_CUDA(m, cudaEventRecord(m->ev_fold[par], m->stream));
+    GEM_CUDA(m, cudaGetLastError());
+    m->ctr_last = m->pipe_ctr[c];
+    memset(&m->stats, 0, sizeof m->stats);
+    m->stats.points_in = n;
     return GEM_OK;
 }
 

@@ -188,6 +188,12 @@ class ElevationMap:
         if rc:
             check(rc, self._h, "gem_add_points")
 
+    def add_stream_fast(self, xyzi_ptr, rgba_ptr, n: int, frame_ref):
+        """gem_add_points_stream: frame-pipelined add of a device-resident cloud"""
+        rc = self._lib.gem_add_points_stream(self._h, xyzi_ptr, rgba_ptr, n, frame_ref)
+        if rc:
+            check(rc, self._h, "gem_add_points_stream")
+
     def add_host_async_fast(self, xyzi_ptr, rgba_ptr, n: int, frame_ref):
         """gem_add_points_host_async: pinned host buffers, H2D on a copy stream overlapped with the
         previous frame's kernels, no host synchronisation"""

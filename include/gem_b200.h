@@ -126,6 +126,14 @@ int gem_add_points(gem_map *m, const void *xyzi_device, const void *rgba_device,
                    const gem_frame *frame);
 int gem_add_points_host(gem_map *m, const void *xyzi_host, const void *rgba_host, int n,
                         const gem_frame *frame);
+/* Stream mode: same result as gem_add_points, but consecutive calls are software-pipelined: the
+ * transform/bin, allocation and scatter kernels of frame i+1 run on a second stream while the
+ * per-cell fold of frame i (the only kernel that touches the layers, and mostly a serial tail)
+ * is still running; scratch is double-buffered.  Contract: the device inputs must already be
+ * complete when the call is made (they are read on an internal stream, not on gem_get_stream)
+ * and must stay valid until the next-but-one call or gem_sync.  n <= max_points. */
+int gem_add_points_stream(gem_map *m, const void *xyzi_device, const void *rgba_device, int n,
+                          const gem_frame *frame);
 /* Several clouds in one launch (multi-sensor rigs, BASELINE config 5): the device buffers hold
  * n_segments clouds back to back, cloud s = points [offsets[s], offsets[s+1]) with its own
  * per-frame constants frames[s] (both host arrays, offsets has n_segments+1 entries,

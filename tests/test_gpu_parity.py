@@ -264,6 +264,34 @@ def test_device_pointer_path_matches_host_path():
     assert g1.stats() == g2.stats()
 
 
+def test_stream_mode_overlapping_frames_matches_oracle():
+    """gem_add_points_stream overlaps frame i+1's front kernels with frame i's fold: 24 frames issued
+    back to back without any synchronisation, with scrolling, must equal the oracle's sequential result"""
+    import torch
+    import ctypes as C
+    scene = synth.make_scene()
+    nf = 6
+    frames = [synth.hdl64_frame(k, scene=scene) for k in range(nf)]
+    fobj = [laser_frame(fr["T"]) for fr in frames]
+    xd = [torch.from_numpy(fr["xyzi"]).cuda() for fr in frames]
+    rd = [torch.from_numpy(fr["rgba"]).cuda() for fr in frames]
+    torch.cuda.synchronize()
+    g, o = both(512, 0.1, compat_box_filter=False)
+    seq = [0, 1, 2, 3, 4, 5, 4, 3, 2, 1, 0, 1, 2, 3, 4, 5, 4, 3, 2, 1, 0, 1, 2, 3]
+    g.add(frames[0]["xyzi"], frames[0]["rgba"], fobj[0])            # mix with the ordinary path
+    for k in seq:
+        g.move(frames[k]["position"])
+        g.add_stream_fast(C.c_void_p(xd[k].data_ptr()), C.c_void_p(rd[k].data_ptr()), frames[k]["xyzi"].shape[0], C.byref(fobj[k]))
+    g.add(xd[2], rd[2], fobj[2])                                     # ordinary path after stream mode
+    g.sync()
+    o.add(frames[0]["xyzi"], frames[0]["rgba"], fobj[0])
+    for k in seq:
+        o.move(frames[k]["position"])
+        o.add(frames[k]["xyzi"], frames[k]["rgba"], fobj[k])
+    o.add(frames[2]["xyzi"], frames[2]["rgba"], fobj[2])
+    assert_layers_equal(g, o, what="stream mode")
+
+
 def test_pipelined_host_ingest_matches_sync_path():
     import torch
     import ctypes as C
