@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) k_scatter_records(const RouteRec *rec, in
     if (key < 0) return;
     const int pos = sc.cellBase[key] + sc.rank[i];
     const RouteRec r = rec[i];
-    sc.recA[pos] = make_uint4((uint32_t)i, __float_as_uint(r.h), __float_as_uint(r.var), r.rgb);
+    sc.recA[pos] = make_uint4((uint32_t)i, __float_as_uint(r.h), __float_as_uint(r.var), with_colour_flag(r.rgb, r.intensity));
     sc.recI[pos] = r.intensity;
 }
 

@@ -17,11 +17,11 @@ __global__ void bench(int K, int variant, float *out, long long *cyc, const floa
             float h = sh[c0 + lane], v = sv[c0 + lane];
             for (int t = 0; t < 32; t++) {
                 float hh = __shfl_sync(0xffffffffu, h, t), vv = __shfl_sync(0xffffffffu, v, t);
-                fold_step(s, hh, vv, 0x010101u, 1.0f, true);
+                fold_step(s, hh, vv, 0x1010101u, 1.0f, true);
             }
         }
     } else if (variant == 1) { // smem broadcast + fold_step
-        for (int t = 0; t < K; t++) fold_step(s, sh[t], sv[t], 0x010101u, 1.0f, true);
+        for (int t = 0; t < K; t++) fold_step(s, sh[t], sv[t], 0x1010101u, 1.0f, true);
     } else if (variant == 2) { // only the Kalman arithmetic, literal reference form
         float e = s.elev, var = s.var;
         for (int t = 0; t < K; t++) {
