@@ -719,11 +719,9 @@ static int pipe_setup(gem_map *m)
         if ((rc = dev_alloc(m, &sc.cnt, nc)) || (rc = dev_alloc(m, &sc.cellBase, nc)) || (rc = dev_alloc(m, &sc.touched, T)) ||
             (rc = dev_alloc(m, &sc.tsmall, T)) || (rc = dev_alloc(m, &sc.tlarge, T / FOLD_SMALL_K + 1)) ||
             (rc = dev_alloc(m, &sc.key, P)) || (rc = dev_alloc(m, &sc.rank, P)) || (rc = dev_alloc(m, &sc.h, P)) ||
-            (rc = dev_alloc(m, &sc.hv, P)) || (rc = dev_alloc(m, &sc.recA, P)) || (rc = dev_alloc(m, &sc.recI, P)) ||
-            (rc = dev_alloc(m, &sc.stamp, nc)))
+            (rc = dev_alloc(m, &sc.hv, P)) || (rc = dev_alloc(m, &sc.recA, P)) || (rc = dev_alloc(m, &sc.recI, P)))
             return rc;
         GEM_CUDA(m, cudaMemsetAsync(sc.cnt, 0, nc * sizeof(int), m->stream));
-        GEM_CUDA(m, cudaMemsetAsync(sc.stamp, 0, nc * sizeof(int), m->stream));
         GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_front[i], cudaEventDisableTiming));
         GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_fold[i], cudaEventDisableTiming));
     }
@@ -751,7 +749,6 @@ int gem_add_points_stream(gem_map *m, const void *xyzi, const void *rgba, int n,
     sc.ctr = m->pipe_ctr[c];
     sc.ctr_next = m->pipe_ctr[(c + 1) % 3];
     sc.tstamp = nullptr;
-    sc.call_id = (int)((i % 0x7ffffffeu) + 1u); // never 0 (the stamps' initial value)
     const FrameParams fp = make_frame(frame);
     PointInput in{};
     in.xyzi = (const float4 *)xyzi;
@@ -770,17 +767,10 @@ int gem_add_points_stream(gem_map *m, const void *xyzi, const void *rgba, int n,
     GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_SCATTER,
                   k_scatter<ATTR_XYZI><<<blocks_for((size_t)n, ADD_BLOCK, 148 * 16), ADD_BLOCK, 0, m->front_stream>>>(a, n, sc));
     GEM_CUDA(m, cudaEventRecord(m->ev_front[par], m->front_stream));
-    // main stream: the fold (the only kernel that touches the layers) also executes the deferred scroll
-    // clears / floors of gem_move
-    RegionOps ro;
-    int rb = 0;
-    if ((rc = take_region_ops(m, ro, rb))) return rc;
+    // main stream: deferred scroll clears / floors, then the fold (the only kernel that touches the layers)
+    if (!m->pending.empty() && (rc = flush_all_pending(m))) return rc;
     GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_front[par], 0));
-    const int fb = blocks_for((size_t)n, ADD_BLOCK, 148 * 8);
-    if (ro.count)
-        GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold_regions<<<fb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, sc, ro, fb));
-    else
-        GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<fb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, sc, 1, 1));
+    GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<blocks_for((size_t)n, ADD_BLOCK, 148 * 8), ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, sc, 1, 1));
     GEM_CUDA(m, cudaEventRecord(m->ev_fold[par], m->stream));
     GEM_CUDA(m, cudaGetLastError());
     m->ctr_last = m->pipe_ctr[c];
