@@ -297,12 +297,21 @@ void call_done(gem_map *m)
     m->ctr_cur ^= 1;
 }
 
+// points per thread in the transform / scatter kernels: one point per thread keeps a frame-sized call
+// (1e5 points, < 1 wave) latency-optimal; large calls get 2 or 4 points per thread so that a thread has
+// several independent DRAM/L2 round trips in flight instead of running 3-4 waves of serial chains
+inline int points_per_thread(int n) { return n >= 600000 ? 4 : (n >= 250000 ? 2 : 1); }
+
 // K2..K4 after the binning kernel of the current chunk
 template <int ATTR>
 int run_group_fold(gem_map *m, const Scratch &sc, const AttrInput &a, int n, bool do_fuse, bool do_lowest)
 {
     GEM_LAUNCH(m, GEM_PROF_ALLOC, launch_pdl(m->pdl, k_alloc_cells, blocks_for((size_t)n, ADD_BLOCK, 148 * 4), ADD_BLOCK, m->stream, sc));
-    GEM_LAUNCH(m, GEM_PROF_SCATTER, launch_pdl(m->pdl, k_scatter<ATTR>, blocks_for((size_t)n, ADD_BLOCK, 148 * 16), ADD_BLOCK, m->stream, a, n, sc));
+    const int U = points_per_thread(n);
+    const int sb = blocks_for((size_t)(n + U - 1) / U, ADD_BLOCK, 148 * 16);
+    if (U == 4) GEM_LAUNCH(m, GEM_PROF_SCATTER, launch_pdl(m->pdl, k_scatter<ATTR, 4>, sb, ADD_BLOCK, m->stream, a, n, sc));
+    else if (U == 2) GEM_LAUNCH(m, GEM_PROF_SCATTER, launch_pdl(m->pdl, k_scatter<ATTR, 2>, sb, ADD_BLOCK, m->stream, a, n, sc));
+    else GEM_LAUNCH(m, GEM_PROF_SCATTER, launch_pdl(m->pdl, k_scatter<ATTR, 1>, sb, ADD_BLOCK, m->stream, a, n, sc));
     GEM_LAUNCH(m, GEM_PROF_FOLD, launch_pdl(m->pdl, k_fold, blocks_for((size_t)n, ADD_BLOCK, 148 * 8), ADD_BLOCK, m->stream, m->geom, m->ml, sc, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
     GEM_CUDA(m, cudaGetLastError());
     call_done(m);
@@ -386,8 +395,14 @@ int add_chunk(gem_map *m, const PointInput &in, const AttrInput &a, int n, const
         call_done(m);
         return GEM_OK;
     }
-    const int pb = blocks_for((size_t)n, ADD_BLOCK, 148 * 16);
-    GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, launch_pdl(m->pdl, k_transform_bin<IN>, pb + rb, ADD_BLOCK, m->stream, m->geom, m->ml, fp, in, n, sc, ro, pb, (float *)nullptr, (float *)nullptr));
+    const int U = points_per_thread(n);
+    const int pb = blocks_for((size_t)(n + U - 1) / U, ADD_BLOCK, 148 * 16);
+    if (U == 4)
+        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, launch_pdl(m->pdl, k_transform_bin<IN, 4>, pb + rb, ADD_BLOCK, m->stream, m->geom, m->ml, fp, in, n, sc, ro, pb, (float *)nullptr, (float *)nullptr));
+    else if (U == 2)
+        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, launch_pdl(m->pdl, k_transform_bin<IN, 2>, pb + rb, ADD_BLOCK, m->stream, m->geom, m->ml, fp, in, n, sc, ro, pb, (float *)nullptr, (float *)nullptr));
+    else
+        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, launch_pdl(m->pdl, k_transform_bin<IN, 1>, pb + rb, ADD_BLOCK, m->stream, m->geom, m->ml, fp, in, n, sc, ro, pb, (float *)nullptr, (float *)nullptr));
     return run_group_fold<ATTR>(m, sc, a, n, true, true);
 }
 
@@ -815,8 +830,11 @@ int gem_add_points_multi(gem_map *m, const void *xyzi, const void *rgba, int n_s
     AttrInput a{};
     a.xyzi = in.xyzi;
     a.rgba = in.rgba;
-    const int pb = blocks_for((size_t)n, ADD_BLOCK, 148 * 32);
-    GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin_multi<<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, st, df, in, n, sc, ro, pb));
+    const int U = points_per_thread(n);
+    const int pb = blocks_for((size_t)(n + U - 1) / U, ADD_BLOCK, 148 * 32);
+    if (U == 4) GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin_multi<4><<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, st, df, in, n, sc, ro, pb));
+    else if (U == 2) GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin_multi<2><<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, st, df, in, n, sc, ro, pb));
+    else GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin_multi<1><<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, st, df, in, n, sc, ro, pb));
     if ((rc = run_group_fold<ATTR_XYZI>(m, sc, a, n, true, true))) return rc;
     memset(&m->stats, 0, sizeof m->stats);
     m->stats.points_in = n;
