@@ -84,6 +84,7 @@ SYMBOLS = {
     "gem_raytracing": (C.c_int, [_P]),
     "gem_opt_move": (C.c_int, [_P, _FP, C.c_float, _FP]),
     "gem_closeloop": (C.c_int, [_P, _FP, C.c_float]),
+    "gem_colourise_points": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _P, C.c_int, C.c_int, C.c_int, _P]),
     "gem_export_layers": (C.c_int, [_P, C.POINTER(_P)]),
     "gem_get_layer": (C.c_int, [_P, C.c_int, _P]),
     "gem_set_layer": (C.c_int, [_P, C.c_int, _P]),

@@ -1082,6 +1082,26 @@ int gem_closeloop(gem_map *m, const float up[2], float height_update)
     return GEM_OK;
 }
 
+int gem_colourise_points(gem_map *m, void *xyzi, int n, const double Tc[12], const double Tl[16], const unsigned char *bgr,
+                         int width, int height, int row_stride, void *rgba_out)
+{
+    if (!m || n < 0 || (n > 0 && (!xyzi || !rgba_out)) || !Tc || !Tl || !bgr || width < 1 || height < 1 || row_stride < 3 * width)
+        return fail(m, GEM_ERR_INVALID, "gem_colourise_points: bad argument");
+    SetDev sd(m->dev);
+    ProjParams pp;
+    for (int i = 0; i < 3; i++) // P_lidar2img = Tcamera * TLidar (ElevationMapping.cpp:347), double, left-to-right sums
+        for (int j = 0; j < 4; j++) {
+            double a = Tc[4 * i + 0] * Tl[0 + j];
+            for (int k = 1; k < 4; k++) a = a + Tc[4 * i + k] * Tl[4 * k + j];
+            pp.P[4 * i + j] = a;
+        }
+    pp.width = width; pp.height = height; pp.row_stride = row_stride;
+    if (n > 0)
+        GEM_LAUNCH(m, GEM_PROF_OTHER, k_colourise<<<blocks_for((size_t)n, 256), 256, 0, m->stream>>>((float4 *)xyzi, n, pp, bgr, (uchar4 *)rgba_out));
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
 int gem_export_layers(gem_map *m, float *host_layers[9])
 {
     if (!m || !host_layers) return GEM_ERR_INVALID;

@@ -304,6 +304,16 @@ class ElevationMap:
         p = (C.c_float * 2)(*[float(v) for v in update_position])
         check(self._lib.gem_closeloop(self._h, p, float(height_update)), self._h, "gem_closeloop")
 
+    def colourise(self, xyzi, T_camera, T_lidar, bgr, rgba_out):
+        """ElevationMapping.cpp:331-381 on the device: xyzi (n,4) float32 device tensor (intensity zeroed for
+        points outside the image), bgr (H,W,3) uint8 device tensor, rgba_out (n,4) uint8 device tensor"""
+        n = int(xyzi.shape[0])
+        tc = (C.c_double * 12)(*[float(v) for v in np.asarray(T_camera, np.float64).reshape(-1)])
+        tl = (C.c_double * 16)(*[float(v) for v in np.asarray(T_lidar, np.float64).reshape(-1)])
+        h, w = int(bgr.shape[0]), int(bgr.shape[1])
+        rc = self._lib.gem_colourise_points(self._h, _ptr(xyzi), n, tc, tl, _ptr(bgr), w, h, 3 * w, _ptr(rgba_out))
+        check(rc, self._h, "gem_colourise_points")
+
     # -- read-out ---------------------------------------------------------------------------
     def export_layers(self, out: dict | None = None):
         """grid_map write-back: dict of 9 (L, L) float32 Fortran-ordered arrays, NaN = empty."""

@@ -179,6 +179,15 @@ int gem_raytracing(gem_map *m);
 int gem_opt_move(gem_map *m, const float opt_p[2], float height_update, float aligned_out[2]);
 int gem_closeloop(gem_map *m, const float update_position[2], float height_update);
 
+/* ---- colourisation of the cloud from the camera image (ElevationMapping.cpp:331-381), the step
+ * right before the fusion path.  T_camera: row-major 3x4 "T.camera", T_lidar: row-major 4x4 "T.lidar"
+ * (kitti_intrinsic.yaml / yq_intrinsic.yaml), bgr: device BGR8 image.  Writes rgba_out (r,g,b,255 or
+ * 0,0,0,0) and zeroes the intensity of points that do not project into the image, exactly like the
+ * reference loop; the reference's debug circle drawing into the image (:372) is not reproduced. */
+int gem_colourise_points(gem_map *m, void *xyzi_device, int n, const double T_camera[12], const double T_lidar[16],
+                         const unsigned char *bgr_device, int width, int height, int row_stride_bytes,
+                         void *rgba_out_device);
+
 /* ---- write-back replacing ElevationMap::show's L*L CPU loop (ElevationMap.cpp:85-149) --
  * Emits 9 float32 layers {elevation, variance, rough, slope, traver, color_r, color_g,
  * color_b, intensity} (ElevationMap.cpp:44) in grid_map::Matrix layout: COLUMN-major,

@@ -803,6 +803,38 @@ void orc_closeloop(orc_map *m, const float up[2], float height_update)
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* colourisation, ElevationMapping.cpp:331-381 (CPU loop of the ROS node)               */
+/* ------------------------------------------------------------------------------------ */
+void orc_colourise(float *xyzi, int n, const double Tc[12], const double Tl[16], const unsigned char *bgr, int width,
+                   int height, int row_stride, unsigned char *rgba_out)
+{
+    double P[12];
+    int i, j, k;
+    for (i = 0; i < 3; i++) /* :347 P_lidar2img = Tcamera * TLidar */
+        for (j = 0; j < 4; j++) {
+            double a = Tc[4 * i + 0] * Tl[0 + j];
+            for (k = 1; k < 4; k++) a = a + Tc[4 * i + k] * Tl[4 * k + j];
+            P[4 * i + j] = a;
+        }
+    for (i = 0; i < n; i++) {
+        double x = (double)xyzi[4 * i], y = (double)xyzi[4 * i + 1], z = (double)xyzi[4 * i + 2];
+        double X = ((P[0] * x + P[1] * y) + P[2] * z) + P[3] * 1.0; /* :351-355 */
+        double Y = ((P[4] * x + P[5] * y) + P[6] * z) + P[7] * 1.0;
+        double Z = ((P[8] * x + P[9] * y) + P[10] * z) + P[11] * 1.0;
+        float Px = (float)(X / Z), Py = (float)(Y / Z); /* :359-360 */
+        int mx = f2i_rz(Px), my = f2i_rz(Py);           /* :364-365 */
+        unsigned char *o = rgba_out + 4 * (size_t)i;
+        if (mx > 0 && mx < width && my > 0 && my < height && Z > 0) { /* :368 */
+            const unsigned char *px = bgr + (size_t)my * row_stride + 3 * (size_t)mx;
+            o[0] = px[2]; o[1] = px[1]; o[2] = px[0]; o[3] = 255;
+        } else { /* :376-381 */
+            o[0] = o[1] = o[2] = o[3] = 0;
+            xyzi[4 * i + 3] = 0;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* multi-threaded CPU baseline (bench.py cpu_baseline / --impl reference only)          */
 /* ------------------------------------------------------------------------------------ */
 typedef struct {

@@ -105,6 +105,13 @@ void orc_raytracing(orc_map *m);
 void orc_optmove(orc_map *m, const float opt_p[2], float height_update, float aligned_out[2]);
 void orc_closeloop(orc_map *m, const float update_position[2], float height_update);
 
+/* ElevationMapping.cpp:331-381: colourise the cloud from a BGR8 image.  xyzi is n x {x,y,z,intensity}
+ * (intensity zeroed for points that do not project into the image), rgba_out n x {r,g,b,a}.
+ * NOT pinned by reference-generated vectors (the reference loop needs OpenCV/ROS); the debug circle the
+ * reference draws into the image after each lookup (:372) is deliberately not restated. */
+void orc_colourise(float *xyzi, int n, const double T_camera[12], const double T_lidar[16], const unsigned char *bgr,
+                   int width, int height, int row_stride, unsigned char *rgba_out);
+
 /* deterministic float trig used by the feature kernel restatement (see .c) */
 float orc_sinf(float a);
 float orc_cosf(float a);

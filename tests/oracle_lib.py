@@ -69,6 +69,7 @@ def load():
         getattr(lib, fn).argtypes = [C.c_float]
     lib.orc_atan2f.restype = C.c_float
     lib.orc_atan2f.argtypes = [C.c_float, C.c_float]
+    lib.orc_colourise.argtypes = [P, C.c_int, P, P, P, C.c_int, C.c_int, C.c_int, P]
     lib.orc_add_points_mt.argtypes = [MP, C.c_int, P, P, P, C.c_double, C.c_double, C.POINTER(OrcSensor), P, C.c_int]
     _lib = lib
     return lib
@@ -76,6 +77,18 @@ def load():
 
 def _p(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def colourise(xyzi, T_camera, T_lidar, bgr):
+    """oracle twin of gem_colourise_points: returns (xyzi with zeroed intensities, rgba)"""
+    lib = load()
+    xyzi = np.array(xyzi, np.float32, copy=True)
+    tc = np.ascontiguousarray(T_camera, np.float64).reshape(-1)
+    tl = np.ascontiguousarray(T_lidar, np.float64).reshape(-1)
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    rgba = np.zeros((xyzi.shape[0], 4), np.uint8)
+    lib.orc_colourise(_p(xyzi), xyzi.shape[0], _p(tc), _p(tl), _p(bgr), bgr.shape[1], bgr.shape[0], 3 * bgr.shape[1], _p(rgba))
+    return xyzi, rgba
 
 
 def sensor_from_frame(frame) -> OrcSensor:

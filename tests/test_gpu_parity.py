@@ -335,6 +335,35 @@ def test_multi_segment_batch_equals_sequential_adds():
     assert multi.stats()["points_in"] == int(off[-1])
 
 
+def test_colourise_matches_oracle_and_feeds_the_fold():
+    """SURVEY 8f row 2 (ElevationMapping.cpp:331-381): KITTI-shaped projection, random image"""
+    import torch
+    import oracle_lib
+    rng = np.random.default_rng(17)
+    W, H = 1241, 376
+    bgr = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+    Tc = np.array([[718.856, 0, 607.1928, 0], [0, 718.856, 185.2157, 0], [0, 0, 1, 0]], np.float64)
+    Tl = np.array([[0, -1, 0, 0.0], [0, 0, -1, -0.08], [1, 0, 0, -0.27], [0, 0, 0, 1]], np.float64)  # lidar x fwd -> camera z
+    fr = synth.hdl64_frame(2)
+    xo, co = oracle_lib.colourise(fr["xyzi"], Tc, Tl, bgr)
+    x = torch.from_numpy(fr["xyzi"].copy()).cuda()
+    c = torch.zeros((x.shape[0], 4), dtype=torch.uint8, device="cuda")
+    img = torch.from_numpy(bgr).cuda()
+    g = gem_b200.ElevationMap(200, 0.1, compat_box_filter=False)
+    torch.cuda.synchronize()
+    g.colourise(x, Tc, Tl, img, c)
+    g.sync()
+    assert np.array_equal(c.cpu().numpy(), co)
+    assert np.array_equal(x.cpu().numpy().view(np.uint32), xo.view(np.uint32))
+    inside = int((co[:, 3] == 255).sum())
+    assert 2000 < inside < x.shape[0] - 2000          # both branches exercised
+    f = laser_frame(fr["T"])
+    o = OracleMap(200, 0.1, compat_box_filter=False)
+    g.add(x, c, f); g.sync()
+    o.add(xo, co, f)
+    assert_layers_equal(g, o, what="colourised cloud fused")
+
+
 def test_pcl_record_ingest():
     fr = synth.hdl64_frame(4)
     n = fr["xyzi"].shape[0]

@@ -295,3 +295,45 @@ def test_mt_baseline_twin_equals_single_thread():
     b.add_mt(fr["xyzi"], fr["rgba"], f, 4)
     for name in ("elevation", "variance", "intensity", "color_r", "color_g", "color_b", "lowest"):
         assert np.array_equal(a.get_layer(name), b.get_layer(name)), name
+
+
+def test_colourise_kats():
+    """ElevationMapping.cpp:331-381: pinhole projection, strict image-bound test, intensity zeroing"""
+    import oracle_lib
+    W, H = 64, 48
+    bgr = np.zeros((H, W, 3), np.uint8)
+    bgr[..., 0] = np.arange(W)[None, :]           # b = column
+    bgr[..., 1] = np.arange(H)[:, None]           # g = row
+    bgr[..., 2] = 200
+    Tc = np.array([[50, 0, 32, 0], [0, 50, 24, 0], [0, 0, 1, 0]], float)     # fx=fy=50, cx=32, cy=24
+    Tl = np.eye(4)
+    pts = np.array([[0, 0, 2, 9],        # centre pixel (32, 24)
+                    [0.2, -0.1, 1, 9],   # (42, 19)
+                    [0, 0, -2, 9],       # behind the camera
+                    [-0.64, 0, 1, 9],    # x = 0 -> rejected (strict > 0)
+                    [0.62, 0, 1, 9],     # x = 63 -> inside
+                    [0.64, 0, 1, 9],     # x = 64 -> rejected (strict < width)
+                    [0.001, 0.001, 1, 9]], np.float32)
+    xyzi, rgba = oracle_lib.colourise(pts, Tc, Tl, bgr)
+    assert rgba[0].tolist() == [200, 24, 32, 255]
+    assert rgba[1].tolist() == [200, 19, 42, 255]
+    for k in (2, 3, 5):
+        assert rgba[k].tolist() == [0, 0, 0, 0] and xyzi[k, 3] == 0
+    assert rgba[4].tolist() == [200, 24, 63, 255] and xyzi[4, 3] == 9
+    assert rgba[6].tolist() == [200, 24, 32, 255]      # truncation toward zero of 32.05, 24.05
+    # independent numpy re-derivation on a random cloud
+    rng = np.random.default_rng(3)
+    cloud = np.concatenate([rng.uniform(-3, 3, (5000, 2)), rng.uniform(-1, 6, (5000, 1)), np.full((5000, 1), 7.0)], 1).astype(np.float32)
+    x2, c2 = oracle_lib.colourise(cloud, Tc, Tl, bgr)
+    P = Tc @ Tl
+    xyz1 = np.concatenate([cloud[:, :3].astype(np.float64), np.ones((5000, 1))], 1)
+    X = ((P[0, 0] * xyz1[:, 0] + P[0, 1] * xyz1[:, 1]) + P[0, 2] * xyz1[:, 2]) + P[0, 3]
+    Y = ((P[1, 0] * xyz1[:, 0] + P[1, 1] * xyz1[:, 1]) + P[1, 2] * xyz1[:, 2]) + P[1, 3]
+    Z = ((P[2, 0] * xyz1[:, 0] + P[2, 1] * xyz1[:, 1]) + P[2, 2] * xyz1[:, 2]) + P[2, 3]
+    with np.errstate(all="ignore"):
+        mx = np.trunc((X / Z).astype(np.float32)).astype(np.int64)
+        my = np.trunc((Y / Z).astype(np.float32)).astype(np.int64)
+    ok = (mx > 0) & (mx < W) & (my > 0) & (my < H) & (Z > 0)
+    assert np.array_equal(c2[:, 3] == 255, ok) and 500 < ok.sum() < 4500
+    assert np.array_equal(c2[ok, 2], bgr[my[ok], mx[ok], 0]) and np.array_equal(c2[ok, 1], bgr[my[ok], mx[ok], 1])
+    assert (x2[~ok, 3] == 0).all() and (x2[ok, 3] == 7).all()
