@@ -439,3 +439,58 @@ def test_headline_config_properties_c2():
     g2.add(fr["xyzi"], fr["rgba"], f)
     g3.add(np.ascontiguousarray(fr["xyzi"][perm]), np.ascontiguousarray(fr["rgba"][perm]), f)
     assert_layers_equal(g2, g3, ["elevation", "variance", "intensity", "color_r", "color_g", "color_b"], what="perm")
+
+
+def test_large_grid_4096_config4_size():
+    """BASELINE config 4 map size (4096x4096 @ 0.05 m) on one GPU: oracle parity on a frame, plus
+    size-independent properties (empty add is idempotent, export round-trips through set_layer)"""
+    L, res = 4096, 0.05
+    fr = synth.hdl64_frame(7)
+    f = laser_frame(fr["T"])
+    g, o = both(L, res, compat_box_filter=False)
+    for m in (g, o):
+        m.move(fr["position"])
+        m.add(fr["xyzi"], fr["rgba"], f)
+    assert_layers_equal(g, o, what="4096^2")
+    before = {n: g.get_layer(n) for n in ("elevation", "variance", "intensity", "color_r", "lowest")}
+    g.add(np.zeros((0, 4), np.float32), None, f, n=0)           # empty cloud: nothing may change
+    for n, a in before.items():
+        assert np.array_equal(a.view(np.uint32) if a.dtype.kind == "f" else a, (g.get_layer(n).view(np.uint32) if a.dtype.kind == "f" else g.get_layer(n))), n
+    # checkpoint / restore (the dead G_get_mapinfo / G_set_mapinfo of gpu.cu:457-475)
+    g2 = gem_b200.ElevationMap(L, res, compat_box_filter=False)
+    g2.move(fr["position"])
+    for n in ("elevation", "variance", "intensity", "color_r", "color_g", "color_b", "traver", "lowest"):
+        g2.set_layer(n, g.get_layer(n))
+    fr2 = synth.hdl64_frame(8)
+    f2 = laser_frame(fr2["T"])
+    for m in (g, g2, o):
+        m.move(fr2["position"])
+        m.add(fr2["xyzi"], fr2["rgba"], f2)
+    assert_layers_equal(g, g2, what="restored map continues identically")
+    assert_layers_equal(g, o, what="4096^2 second frame")
+
+
+def test_error_paths_return_codes():
+    import ctypes as C
+    from gem_b200 import _lib
+    lib = _lib.load()
+    g = gem_b200.ElevationMap(64, 0.1)
+    f = laser_frame(np.eye(4))
+    assert lib.gem_add_points(g.handle, None, None, 5, C.byref(f)) == 1            # null cloud
+    assert b"bad argument" in lib.gem_last_error(g.handle)
+    assert lib.gem_add_points(g.handle, None, None, -1, C.byref(f)) == 1
+    assert lib.gem_get_layer(g.handle, 99, None) == 1
+    assert lib.gem_add_points_multi(g.handle, None, None, 0, None, None) == 1
+    assert lib.gem_fuse_records_counted(g.handle, None, None, 0, 0) == 1
+    t = gem_b200.ElevationMap(64, 0.1, tile=(0, 64, 0, 32))
+    with pytest.raises(gem_b200.GemError):
+        t.compute_features()                                                         # tiled handles: not implemented
+    with pytest.raises(gem_b200.GemError):
+        gem_b200.ElevationMap(64, 0.1, tile=(0, 64, 40, 32))                        # tile outside the map
+    big = np.zeros((10, 4), np.float32)
+    g3 = gem_b200.ElevationMap(64, 0.1, max_points=4)
+    with pytest.raises(gem_b200.GemError):
+        import torch
+        x = torch.from_numpy(big).cuda()
+        g3.add_stream_fast(C.c_void_p(x.data_ptr()), None, 10, C.byref(f))          # n > max_points in stream mode
+    g3.add(big, None, f)                                                             # chunked path copes
