@@ -487,10 +487,10 @@ def test_error_paths_return_codes():
         t.compute_features()                                                         # tiled handles: not implemented
     with pytest.raises(gem_b200.GemError):
         gem_b200.ElevationMap(64, 0.1, tile=(0, 64, 40, 32))                        # tile outside the map
-    big = np.zeros((10, 4), np.float32)
-    g3 = gem_b200.ElevationMap(64, 0.1, max_points=4)
+    big = np.zeros((1000, 4), np.float32)
+    g3 = gem_b200.ElevationMap(64, 0.1, max_points=4)          # raised internally to nc/32+1 = 129
     with pytest.raises(gem_b200.GemError):
         import torch
         x = torch.from_numpy(big).cuda()
-        g3.add_stream_fast(C.c_void_p(x.data_ptr()), None, 10, C.byref(f))          # n > max_points in stream mode
+        g3.add_stream_fast(C.c_void_p(x.data_ptr()), None, 1000, C.byref(f))        # n > max_points in stream mode
     g3.add(big, None, f)                                                             # chunked path copes
