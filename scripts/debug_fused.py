@@ -36,8 +36,7 @@ print(g.stats())
 g.move(frames[1]["position"]); g.add(xd[1], rd[1], fobjs[1]); g.sync()
 st = g.debug_phase_stamps(True)
 print("phase stamps (us from start):", [round((t - st[0]) / 1e3, 2) for t in st[:11]])
-print("slowest long list: ns", st[11] >> 20, "k", st[11] & 0xfffff, " last block end us", (st[9]-st[0])/1e3)
-print("one long list: k", st[15], "load_idx ns", st[12], "rank ns", st[13], "total ns", st[14])
+print("last block end us", (st[9] - st[0]) / 1e3)
 pr_names = ["transform", "sync1", "alloc", "sync2", "scatter", "sync3", "fold_large", "fold_small"]
 print({n: round((st[i + 1] - st[i]) / 1e3, 2) for i, n in enumerate(pr_names)})
 g.profile_enable(True)
