@@ -183,7 +183,7 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, W = args.steps, args.warmup
     L, res = 1024 * world, 0.05
-    F = int(min(max(K + W + 2, 8), args.frames))
+    F = int(max(2, args.frames))   # per-GPU inputs larger than L2 whatever --steps is
     # every rank drives its own sensor: same scene generator, different seeds/poses
     frames = gen_frames(F, first=1000 * rank)
     ox, oy = sensor_offset(rank, world)
