@@ -97,6 +97,9 @@ SYMBOLS = {
     "gem_host_free": (C.c_int, [_P]),
     "gem_route_points": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame), C.c_int, C.c_int, _P, _P, C.c_int]),
     "gem_fuse_records": (C.c_int, [_P, _P, C.c_int]),
+    "gem_get_layer_device": (C.c_int, [_P, C.c_int, _P]),
+    "gem_compute_features_tiled": (C.c_int, [_P, _P]),
+    "gem_raytracing_tiled": (C.c_int, [_P, _P]),
     "gem_route_points_peer": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame), C.c_int, C.c_int,
                                         C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int, C.c_int]),
     "gem_fuse_records_counted": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),

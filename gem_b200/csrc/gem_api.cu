@@ -55,6 +55,7 @@ struct gem_map {
     float *d_int = nullptr;
     float *d_out = nullptr; // 9 * nc floats read-out staging
     int *d_owner_cnt = nullptr;
+    uint32_t *d_gbitmap = nullptr; // tiled ray clean-up: validity bitmap of the map-wide lowest layer
     Counters *h_ctr = nullptr; // pinned
     // pipelined host ingest (gem_add_points_host_async)
     cudaStream_t copy_stream = nullptr;
@@ -993,10 +994,10 @@ int gem_var_update(gem_map *m, float dv)
 int gem_compute_features(gem_map *m)
 {
     if (!m) return GEM_ERR_INVALID;
-    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_compute_features: tiled handles need a halo exchange (not implemented)");
+    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_compute_features: tiled handles take the halo-padded tile: use gem_compute_features_tiled");
     SetDev sd(m->dev);
     { int rcf = flush_for_observer(m); if (rcf) return rcf; }
-    GEM_LAUNCH(m, GEM_PROF_FEATURES, k_features<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml));
+    GEM_LAUNCH(m, GEM_PROF_FEATURES, k_features<false><<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, nullptr));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }
@@ -1027,10 +1028,52 @@ int gem_map_feature(gem_map *m, float *elevation, float *var, int *R, int *G, in
     return GEM_OK;
 }
 
+int gem_get_layer_device(gem_map *m, int layer, void *out_device)
+{
+    if (!m || !out_device || layer < 0 || layer > 10) return fail(m, GEM_ERR_INVALID, "gem_get_layer_device: bad argument");
+    SetDev sd(m->dev);
+    { int rcf = flush_for_observer(m); if (rcf) return rcf; }
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_unpack_layer<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, layer, out_device));
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
+int gem_compute_features_tiled(gem_map *m, const float *padded_elevation)
+{
+    if (!m || !padded_elevation) return fail(m, GEM_ERR_INVALID, "gem_compute_features_tiled: bad argument");
+    if (!m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_compute_features_tiled: handle is not tiled");
+    SetDev sd(m->dev);
+    { int rcf = flush_for_observer(m); if (rcf) return rcf; }
+    GEM_LAUNCH(m, GEM_PROF_FEATURES, k_features<true><<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, padded_elevation));
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
+int gem_raytracing_tiled(gem_map *m, const float *global_lowest)
+{
+    if (!m || !global_lowest) return fail(m, GEM_ERR_INVALID, "gem_raytracing_tiled: bad argument");
+    if (!m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_raytracing_tiled: handle is not tiled");
+    SetDev sd(m->dev);
+    { int rcf = flush_for_observer(m); if (rcf) return rcf; }
+    const size_t ng = (size_t)m->L * m->L;
+    if (!m->d_gbitmap) { int rc = dev_alloc(m, &m->d_gbitmap, ng / 32 + 1); if (rc) return rc; }
+    int *ray_count = &m->ctr_buf[m->ctr_cur ^ 1]->pad4[0];
+    GEM_CUDA(m, cudaMemsetAsync(ray_count, 0, sizeof(int), m->stream));
+    MapLayers mlg = m->ml;
+    mlg.lowest = const_cast<float *>(global_lowest); // rays probe the replicated, map-wide lowest layer
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_collect<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, m->cfg.obstacle_threshold, m->sc.cellBase, ray_count));
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_lowest_bitmap<<<blocks_for(ng, 256, 1 << 30), 256, 0, m->stream>>>(global_lowest, (int)ng, m->d_gbitmap));
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_trace<<<148 * 8, 256, 0, m->stream>>>(m->geom, mlg, m->d_gbitmap, m->sensorZ, m->sc.cellBase, ray_count));
+    GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml.lowest, m->nc, 10.0f)); // own tile's lowest
+    GEM_CUDA(m, cudaGetLastError());
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return GEM_OK;
+}
+
 int gem_raytracing(gem_map *m)
 {
     if (!m) return GEM_ERR_INVALID;
-    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_raytracing: tiled handles need replicated lowest (not implemented)");
+    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_raytracing: tiled handles take the map-wide lowest layer: use gem_raytracing_tiled");
     SetDev sd(m->dev);
     { int rcf = flush_for_observer(m); if (rcf) return rcf; }
     // ray list lives in cellBase (free between add calls), its length in the spare counter buffer

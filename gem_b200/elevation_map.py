@@ -373,6 +373,17 @@ class ElevationMap:
                                         _ptr(rec_out), _ptr(counts_out), int(bucket_stride))
         check(rc, self._h, "gem_route_points")
 
+    def get_layer_device(self, name: str, out):
+        """dense (rows, cols) copy of a layer into a device tensor (float32, int32 for colours)"""
+        lid = 10 if name == "traver_out" else _lib.LAYERS[name]
+        check(self._lib.gem_get_layer_device(self._h, lid, _ptr(out)), self._h, "gem_get_layer_device")
+
+    def compute_features_tiled(self, padded_elevation):
+        check(self._lib.gem_compute_features_tiled(self._h, _ptr(padded_elevation)), self._h, "gem_compute_features_tiled")
+
+    def raytracing_tiled(self, global_lowest):
+        check(self._lib.gem_raytracing_tiled(self._h, _ptr(global_lowest)), self._h, "gem_raytracing_tiled")
+
     def route_points_peer(self, xyzi, rgba, frame: GemFrame, tiles_r: int, tiles_c: int, peer_recv, peer_counts,
                           my_rank: int, bucket_stride: int):
         """peer_recv / peer_counts: lists of device addresses (ints), one per rank"""

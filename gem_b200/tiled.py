@@ -43,6 +43,52 @@ def owner_of(gx, gy, world: int, L: int):
     return (np.asarray(gx) // th) * tc + np.asarray(gy) // tw
 
 
+def border_pack(elev):
+    """the four 2-cell border strips of a (rows, cols) tile, flattened: top, bottom, left, right"""
+    import torch
+    return torch.cat([elev[:2].reshape(-1), elev[-2:].reshape(-1), elev[:, :2].reshape(-1), elev[:, -2:].reshape(-1)])
+
+
+def padded_from_borders(own, borders, rank: int, world: int):
+    """(rows+4, cols+4) elevation of tile `rank` with the 2-cell halo the 5x5 feature stencil reads
+    (gpu_process.cu:590-616), cut from every rank's border_pack(); -10 (the empty sentinel) outside the map."""
+    import torch
+    rows, cols = own.shape
+    tr, tc = plan_tiles(world)
+    i, j = rank // tc, rank % tc
+    out = torch.full((rows + 4, cols + 4), -10.0, dtype=own.dtype, device=own.device)
+    out[2:-2, 2:-2] = own
+
+    def strips(r):
+        b = borders[r]
+        top, bottom = b[:2 * cols].view(2, cols), b[2 * cols:4 * cols].view(2, cols)
+        left, right = b[4 * cols:4 * cols + 2 * rows].view(rows, 2), b[4 * cols + 2 * rows:].view(rows, 2)
+        return top, bottom, left, right
+
+    for di in (-1, 0, 1):
+        for dj in (-1, 0, 1):
+            ni, nj = i + di, j + dj
+            if (di == 0 and dj == 0) or not (0 <= ni < tr and 0 <= nj < tc):
+                continue
+            top, bottom, left, right = strips(ni * tc + nj)
+            rs = slice(0, 2) if di < 0 else slice(rows + 2, rows + 4) if di > 0 else slice(2, rows + 2)
+            cs = slice(0, 2) if dj < 0 else slice(cols + 2, cols + 4) if dj > 0 else slice(2, cols + 2)
+            if di == 0:
+                src = right if dj < 0 else left                       # rows x 2
+            else:
+                band = bottom if di < 0 else top                      # 2 x cols
+                src = band if dj == 0 else band[:, -2:] if dj < 0 else band[:, :2]
+            out[rs, cs] = src
+    return out
+
+
+def global_from_tiles(tiles, world: int, L: int):
+    """stitch equally sized per-rank (rows, cols) tiles (rank order) into the (L, L) geographic array"""
+    import torch
+    tr, tc = plan_tiles(world)
+    return torch.cat([torch.cat(list(tiles[i * tc:(i + 1) * tc]), dim=1) for i in range(tr)], dim=0).contiguous()
+
+
 def exchange(send_rec, send_counts, group=None):
     """all-to-all of variable-size record buckets.
 
@@ -154,6 +200,41 @@ class TiledElevationMap:
 
     def map_capacity(self):
         return self.send.shape[0]
+
+    def _equal_tiles(self):
+        if self.L % self.tiles_r or self.L % self.tiles_c:
+            raise ValueError("features / clean-up on a tiled map need L divisible by the tile grid")
+        return self.tile[1], self.tile[3]
+
+    def compute_features(self):
+        """Map_feature on the tiled map: all-gather the tiles' 2-cell elevation borders (a few KB per rank),
+        build the halo-padded tile and run the 5x5 PCA kernel on it.  Equal to the single-GPU result cell for cell."""
+        import torch
+        import torch.distributed as dist
+        rows, cols = self._equal_tiles()
+        with torch.cuda.stream(self.stream):
+            own = torch.empty((rows, cols), dtype=torch.float32, device=self.dev)
+            self.map.get_layer_device("elevation", own)
+            mine = border_pack(own)
+            allb = torch.empty((self.world, mine.numel()), dtype=torch.float32, device=self.dev)
+            dist.all_gather_into_tensor(allb, mine)
+            padded = padded_from_borders(own, allb, self.rank, self.world).contiguous()
+            self.map.compute_features_tiled(padded)
+            self._keep_feat = (own, allb, padded)
+
+    def clean(self):
+        """Raytracing on the tiled map: a ray may cross any tile, so the per-frame `lowest` layer is replicated
+        (one all-gather of L*L floats) and each rank traces the rays that START in its tile."""
+        import torch
+        import torch.distributed as dist
+        rows, cols = self._equal_tiles()
+        with torch.cuda.stream(self.stream):
+            own = torch.empty((rows, cols), dtype=torch.float32, device=self.dev)
+            self.map.get_layer_device("lowest", own)
+            allt = torch.empty((self.world, rows, cols), dtype=torch.float32, device=self.dev)
+            dist.all_gather_into_tensor(allt, own)
+            glob = global_from_tiles(list(allt), self.world, self.L)
+            self.map.raytracing_tiled(glob)
 
     def get_layer(self, name):
         return self.map.get_layer(name)

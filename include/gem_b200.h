@@ -244,6 +244,18 @@ int gem_route_points(gem_map *m, const void *xyzi_device, const void *rgba_devic
                      const gem_frame *frame, int tiles_r, int tiles_c, void *rec_out_device,
                      int *counts_out_device, int bucket_stride);
 int gem_fuse_records(gem_map *m, const void *rec_device, int n);
+/* ---- features / ray clean-up on tiled handles (halo + replicated lowest) ---------------
+ * gem_get_layer_device: dense rows*cols copy of one layer into device memory (float, or int32 for the
+ *   colour ids; id 10 = the traversability output of the last feature pass), e.g. to cut halo strips.
+ * gem_compute_features_tiled: Map_feature's kernel on a tile; padded_elevation_device is the tile's
+ *   elevation with a 2-cell halo from the neighbouring tiles, (tile_rows+4) x (tile_cols+4) row-major,
+ *   -10 outside the map.  Results equal the untiled map's, cell for cell.
+ * gem_raytracing_tiled: Raytracing on a tile; global_lowest_device is the map-wide L x L lowest layer
+ *   (every rank's tile of it gathered); resets the OWN tile's lowest to 10 afterwards. */
+int gem_get_layer_device(gem_map *m, int layer, void *out_device);
+int gem_compute_features_tiled(gem_map *m, const float *padded_elevation_device);
+int gem_raytracing_tiled(gem_map *m, const float *global_lowest_device);
+
 /* Peer-memory routing (no collective library on the data path): like gem_route_points with a bucket
  * stride, but every record is stored directly into the OWNING rank's receive buffer through a peer
  * mapping (NVLink/NVSwitch): rank r's records for owner o go to peer_recv[o] + r*bucket_stride, its

@@ -34,17 +34,28 @@ tm = tiled.TiledElevationMap(L, res, max_points=1 << 20, bucket_capacity=0 if mo
 for s in range(steps):
     fr, f = cloud(rank, s)
     tm.add(torch.from_numpy(fr["xyzi"]).to(dev), torch.from_numpy(fr["rgba"]).to(dev), f)
+pos = np.array([0.0, 0.0, 1.8], np.float32)
+tm.map.move(pos)
+tm.compute_features()      # halo all-gather + 5x5 PCA on the padded tile
+tm.clean()                 # replicated lowest + ray clean-up of the own tile
 tm.map.sync()
 torch.cuda.synchronize()
 ok = True
+NAMES = ("elevation", "variance", "intensity", "color_r", "traver", "rough", "slope", "lowest")
 if rank == 0:
     single = gem_b200.ElevationMap(L, res, compat_box_filter=False)
-    for s in range(steps):
-        for r in range(world):      # per step: source rank order
-            fr, f = cloud(r, s)
-            single.add(fr["xyzi"], fr["rgba"], f)
-    full = {n: single.get_layer(n) for n in ("elevation", "variance", "intensity", "color_r")}
-for name in ("elevation", "variance", "intensity", "color_r"):
+    single.move(pos)
+    for s in range(steps):          # per step ONE multi-sensor frame: the ranks' clouds in rank order
+        cl = [cloud(r, s) for r in range(world)]
+        xa = torch.cat([torch.from_numpy(c[0]["xyzi"]) for c in cl]).to(dev)
+        ca = torch.cat([torch.from_numpy(c[0]["rgba"]) for c in cl]).to(dev)
+        offs = np.concatenate([[0], np.cumsum([c[0]["xyzi"].shape[0] for c in cl])])
+        single.add_multi(xa, ca, offs, [c[1] for c in cl])
+        single.sync()
+    single.compute_features()
+    single.raytracing()
+    full = {n: single.get_layer(n) for n in NAMES}
+for name in NAMES:
     mine = torch.from_numpy(tm.get_layer(name).astype(np.float32).copy()).to(dev)
     gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
     dist.gather(mine, gathered, dst=0)

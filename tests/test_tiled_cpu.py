@@ -71,3 +71,22 @@ def test_exchange_order_gloo_world2(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     got = sum(np.load(tmp_path / f"recv{r}.npy").shape[0] for r in range(2))
     assert got > 9000
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_halo_assembly_matches_slicing(world):
+    """padded_from_borders / global_from_tiles (features and ray clean-up on tiled maps) against plain slicing"""
+    import torch
+    L = 16
+    g = torch.arange(L * L, dtype=torch.float32).view(L, L)
+    tiles = []
+    for r in range(world):
+        r0, nr, c0, nc = tiled.tile_of_rank(r, world, L)
+        tiles.append(g[r0:r0 + nr, c0:c0 + nc].contiguous())
+    assert torch.equal(tiled.global_from_tiles(tiles, world, L), g)
+    borders = torch.stack([tiled.border_pack(t) for t in tiles])
+    gp = torch.full((L + 4, L + 4), -10.0)
+    gp[2:-2, 2:-2] = g
+    for r in range(world):
+        r0, nr, c0, nc = tiled.tile_of_rank(r, world, L)
+        assert torch.equal(tiled.padded_from_borders(tiles[r], borders, r, world), gp[r0:r0 + nr + 4, c0:c0 + nc + 4])
