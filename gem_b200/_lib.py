@@ -27,6 +27,7 @@ class GemConfig(C.Structure):
         ("obstacle_threshold", C.c_float), ("compat_box_filter", C.c_int), ("max_points", C.c_int),
         ("device", C.c_int), ("stream", C.c_void_p),
         ("tile_row0", C.c_int), ("tile_rows", C.c_int), ("tile_col0", C.c_int), ("tile_cols", C.c_int),
+        ("grid_resolution", C.c_double),
     ]
 
 
@@ -97,6 +98,10 @@ SYMBOLS = {
     "gem_host_free": (C.c_int, [_P]),
     "gem_route_points": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame), C.c_int, C.c_int, _P, _P, C.c_int]),
     "gem_fuse_records": (C.c_int, [_P, _P, C.c_int]),
+    "gem_export_orthomosaic": (C.c_int, [_P, _P]),
+    "gem_export_visual_points": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_int)]),
+    "gem_snapshot_shown": (C.c_int, [_P]),
+    "gem_harvest_scrolled_out": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, C.c_int, C.POINTER(C.c_int)]),
     "gem_get_layer_device": (C.c_int, [_P, C.c_int, _P]),
     "gem_compute_features_tiled": (C.c_int, [_P, _P]),
     "gem_raytracing_tiled": (C.c_int, [_P, _P]),

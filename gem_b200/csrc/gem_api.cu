@@ -8,6 +8,8 @@
 // parameters instead of cudaMemcpyTo/FromSymbol round trips, int status codes.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -55,6 +57,12 @@ struct gem_map {
     float *d_int = nullptr;
     float *d_out = nullptr; // 9 * nc floats read-out staging
     int *d_owner_cnt = nullptr;
+    float2 *prev_ev = nullptr;     // gem_snapshot_shown: prevMap_ (ElevationMapping.cpp:422) on the device
+    uint2 *prev_ci = nullptr;
+    float *prev_tr = nullptr;
+    MapGeom prev_geom{};
+    bool prev_valid = false;
+    int *d_viscnt = nullptr;       // visual-cloud export: per (column, row chunk) counts / offsets
     uint32_t *d_gbitmap = nullptr; // tiled ray clean-up: validity bitmap of the map-wide lowest layer
     Counters *h_ctr = nullptr; // pinned
     // pipelined host ingest (gem_add_points_host_async)
@@ -410,6 +418,33 @@ int add_chunk(gem_map *m, const PointInput &in, const AttrInput &a, int n, const
 } // namespace
 
 // =========================================================================================
+static GridMapFrame grid_frame(const gem_map *m, float cx, float cy, int sx, int sy)
+{
+    GridMapFrame f;
+    f.res = m->cfg.grid_resolution > 0.0 ? m->cfg.grid_resolution : (double)m->cfg.resolution;
+    f.half = 0.5 * ((double)m->L * f.res) - 0.5 * f.res;
+    f.cx = (double)cx; f.cy = (double)cy;
+    f.L = m->L; f.sx = sx; f.sy = sy;
+    return f;
+}
+
+// count -> scan -> write of the cells Src takes, in GridMapIterator order; returns the total through *total_out
+template <class Src> static int compact_cells(gem_map *m, const Src &src, int capacity, int *total_out)
+{
+    const int L = m->L;
+    int rc;
+    if (!m->d_viscnt) { if ((rc = dev_alloc(m, &m->d_viscnt, (size_t)L * VIS_WARPS + 1))) return rc; }
+    int *d_total = m->d_viscnt + (size_t)L * VIS_WARPS;
+    const int blocks = (L + 31) / 32;
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_count<Src><<<blocks, 1024, 0, m->stream>>>(src, L, m->d_viscnt));
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_scan<<<1, 1024, 0, m->stream>>>(m->d_viscnt, L * VIS_WARPS, d_total));
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_write<Src><<<blocks, 1024, 0, m->stream>>>(src, L, m->d_viscnt, capacity));
+    GEM_CUDA(m, cudaGetLastError());
+    GEM_CUDA(m, cudaMemcpyAsync(total_out, d_total, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return GEM_OK;
+}
+
 extern "C" {
 
 int gem_version(void) { return GEM_B200_VERSION; }
@@ -1160,6 +1195,97 @@ int gem_export_layers(gem_map *m, float *host_layers[9])
         if (host_layers[k])
             GEM_CUDA(m, cudaMemcpyAsync(host_layers[k], m->d_out + (size_t)k * m->nc, m->nc * 4, cudaMemcpyDeviceToHost, m->stream));
     GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return GEM_OK;
+}
+
+int gem_export_orthomosaic(gem_map *m, unsigned char *host_bgr)
+{
+    if (!m || !host_bgr) return fail(m, GEM_ERR_INVALID, "gem_export_orthomosaic: null argument");
+    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_export_orthomosaic: not available on tiled handles");
+    SetDev sd(m->dev);
+    int rc = ensure_out_staging(m);
+    if (rc) return rc;
+    if ((rc = flush_for_observer(m))) return rc;
+    unsigned char *d_img = reinterpret_cast<unsigned char *>(m->d_out);
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_orthomosaic<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, d_img));
+    GEM_CUDA(m, cudaGetLastError());
+    GEM_CUDA(m, cudaMemcpyAsync(host_bgr, d_img, m->nc * 3, cudaMemcpyDeviceToHost, m->stream));
+    GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return GEM_OK;
+}
+
+int gem_export_visual_points(gem_map *m, float *host_xyz, unsigned char *host_rgb, int capacity, int *count_out)
+{
+    if (!m || !count_out || capacity < 0 || (capacity > 0 && (!host_xyz || !host_rgb)))
+        return fail(m, GEM_ERR_INVALID, "gem_export_visual_points: bad argument");
+    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_export_visual_points: not available on tiled handles");
+    SetDev sd(m->dev);
+    int rc = ensure_out_staging(m);
+    if (rc) return rc;
+    if ((rc = flush_for_observer(m))) return rc;
+    // staging (9 floats per cell): xyz = 3 floats per cell, rgb = 3 bytes per cell behind it
+    VisualSrc src;
+    src.ml = m->ml;
+    src.f = grid_frame(m, m->geom.cx, m->geom.cy, m->geom.sx, m->geom.sy);
+    src.xyz = m->d_out;
+    src.rgb = reinterpret_cast<unsigned char *>(m->d_out + 3 * m->nc);
+    const int cap = (int)std::min<size_t>((size_t)capacity, m->nc);
+    int total = 0;
+    if ((rc = compact_cells(m, src, cap, &total))) return rc;
+    *count_out = total; // the number of shown cells; only min(total, capacity) points are written
+    const size_t n = (size_t)std::min(total, cap);
+    if (n) {
+        GEM_CUDA(m, cudaMemcpyAsync(host_xyz, src.xyz, n * 12, cudaMemcpyDeviceToHost, m->stream));
+        GEM_CUDA(m, cudaMemcpyAsync(host_rgb, src.rgb, n * 3, cudaMemcpyDeviceToHost, m->stream));
+        GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    }
+    return GEM_OK;
+}
+
+int gem_snapshot_shown(gem_map *m)
+{
+    if (!m) return GEM_ERR_INVALID;
+    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_snapshot_shown: not available on tiled handles");
+    SetDev sd(m->dev);
+    int rc;
+    if ((rc = flush_for_observer(m))) return rc;
+    if (!m->prev_ev) {
+        if ((rc = dev_alloc(m, &m->prev_ev, m->nc)) || (rc = dev_alloc(m, &m->prev_ci, m->nc)) || (rc = dev_alloc(m, &m->prev_tr, m->nc))) return rc;
+    }
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_snapshot_shown<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, m->prev_ev, m->prev_ci, m->prev_tr));
+    GEM_CUDA(m, cudaGetLastError());
+    m->prev_geom = m->geom;
+    m->prev_valid = true;
+    return GEM_OK;
+}
+
+int gem_harvest_scrolled_out(gem_map *m, const float current_xy[2], const float shift_xy[2], void *host_points32,
+                             int capacity, int *count_out)
+{
+    if (!m || !current_xy || !shift_xy || !count_out || capacity < 0 || (capacity > 0 && !host_points32))
+        return fail(m, GEM_ERR_INVALID, "gem_harvest_scrolled_out: bad argument");
+    if (!m->prev_valid) return fail(m, GEM_ERR_INVALID, "gem_harvest_scrolled_out: no snapshot (call gem_snapshot_shown first)");
+    SetDev sd(m->dev);
+    int rc = ensure_out_staging(m);
+    if (rc) return rc;
+    HarvestSrc src;
+    src.pev = m->prev_ev; src.pci = m->prev_ci; src.ptr = m->prev_tr;
+    src.f = grid_frame(m, m->prev_geom.cx, m->prev_geom.cy, m->prev_geom.sx, m->prev_geom.sy);
+    // :727-734: current_x (float) -+ length_ * resolution_ / 2 with the node's double resolution_
+    const double halfwin = (double)m->L * src.f.res / 2;
+    src.lox = (double)current_xy[0] - halfwin; src.hix = (double)current_xy[0] + halfwin;
+    src.loy = (double)current_xy[1] - halfwin; src.hiy = (double)current_xy[1] + halfwin;
+    src.dx = shift_xy[0]; src.dy = shift_xy[1];
+    src.out = reinterpret_cast<float4 *>(m->d_out); // 8 of the 9 staging floats per cell
+    const int cap = (int)std::min<size_t>((size_t)capacity, m->nc);
+    int total = 0;
+    if ((rc = compact_cells(m, src, cap, &total))) return rc;
+    *count_out = total;
+    const size_t n = (size_t)std::min(total, cap);
+    if (n) {
+        GEM_CUDA(m, cudaMemcpyAsync(host_points32, src.out, n * 32, cudaMemcpyDeviceToHost, m->stream));
+        GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+    }
     return GEM_OK;
 }
 

@@ -110,7 +110,7 @@ class ElevationMap:
 
     def __init__(self, length: int, resolution: float, mahalanobis_threshold: float = 2.5,
                  obstacle_threshold: float = 0.7, compat_box_filter: bool = True, max_points: int = 0,
-                 device: int = -1, stream=None, tile=None):
+                 device: int = -1, stream=None, tile=None, grid_resolution: float = 0.0):
         self._lib = _lib.load()
         cfg = GemConfig()
         cfg.length = int(length)
@@ -121,6 +121,7 @@ class ElevationMap:
         cfg.max_points = int(max_points)
         cfg.device = int(device)
         cfg.stream = stream
+        cfg.grid_resolution = float(grid_resolution)   # the node's double resolution_ (grid_map positions); 0 = float one
         if tile is not None:
             cfg.tile_row0, cfg.tile_rows, cfg.tile_col0, cfg.tile_cols = [int(v) for v in tile]
         self._h = C.c_void_p()
@@ -372,6 +373,39 @@ class ElevationMap:
         rc = self._lib.gem_route_points(self._h, _ptr(xyzi), _ptr(rgba), n, C.byref(frame), int(tiles_r), int(tiles_c),
                                         _ptr(rec_out), _ptr(counts_out), int(bucket_stride))
         check(rc, self._h, "gem_route_points")
+
+    def export_orthomosaic(self) -> np.ndarray:
+        """bgr8 orthomosaic of ElevationMap::show (ElevationMap.cpp:87,123-125), (L, L, 3) uint8"""
+        img = np.empty((self.length, self.length, 3), np.uint8)
+        check(self._lib.gem_export_orthomosaic(self._h, _ptr(img)), self._h, "gem_export_orthomosaic")
+        return img
+
+    def export_visual_points(self, capacity: int = -1):
+        """visual cloud of ElevationMap::show (ElevationMap.cpp:112-121): (xyz float32 (n,3), rgb uint8 (n,3))"""
+        cap = self.ncells if capacity < 0 else int(capacity)
+        xyz = np.empty((max(cap, 1), 3), np.float32)
+        rgb = np.empty((max(cap, 1), 3), np.uint8)
+        cnt = C.c_int()
+        check(self._lib.gem_export_visual_points(self._h, _ptr(xyz), _ptr(rgb), cap, C.byref(cnt)), self._h,
+              "gem_export_visual_points")
+        n = min(cnt.value, cap)
+        return xyz[:n], rgb[:n], cnt.value
+
+    def snapshot_shown(self):
+        """prevMap_ = map_.visualMap_ (ElevationMapping.cpp:422), kept on the device"""
+        check(self._lib.gem_snapshot_shown(self._h), self._h, "gem_snapshot_shown")
+
+    def harvest_scrolled_out(self, current_xy, shift_xy, capacity: int = -1):
+        """ElevationMapping.cpp:716-765: (n, 8) float32 PointXYZRGBICT records of the snapshot's cells that left the
+        window, plus the total count"""
+        cap = self.ncells if capacity < 0 else int(capacity)
+        out = np.empty((max(cap, 1), 8), np.float32)
+        cur = (C.c_float * 2)(*[float(v) for v in current_xy])
+        sh = (C.c_float * 2)(*[float(v) for v in shift_xy])
+        cnt = C.c_int()
+        check(self._lib.gem_harvest_scrolled_out(self._h, cur, sh, _ptr(out), cap, C.byref(cnt)), self._h,
+              "gem_harvest_scrolled_out")
+        return out[:min(cnt.value, cap)], cnt.value
 
     def get_layer_device(self, name: str, out):
         """dense (rows, cols) copy of a layer into a device tensor (float32, int32 for colours)"""

@@ -59,6 +59,10 @@ typedef struct gem_config {
     /* spatial tile owned by this handle (multi-GPU tiling).  All zero = whole
      * map.  Tiled handles do not scroll (gem_move keeps start index 0). */
     int tile_row0, tile_rows, tile_col0, tile_cols;
+    /* The node keeps its resolution as a double (ElevationMapping.hpp:314) and grid_map computes cell-centre
+     * positions with it, while the CUDA side gets the float.  Used only for the positions emitted by
+     * gem_export_visual_points / gem_harvest_scrolled_out; 0 = (double)resolution. */
+    double grid_resolution;
 } gem_config;
 
 enum { GEM_SENSOR_LASER = 0, GEM_SENSOR_STRUCTURED_LIGHT = 1 };
@@ -194,6 +198,28 @@ int gem_colourise_points(gem_map *m, void *xyzi_device, int n, const double T_ca
  * storage indexed, NaN where the reference leaves the cell cleared (elevation == -10 or
  * traver == -10 or traver is NaN, ElevationMap.cpp:101).  host_layers[k] may be NULL. */
 int gem_export_layers(gem_map *m, float *host_layers[9]);
+
+/* The other two products of ElevationMap::show, from the same pass's state (call after gem_compute_features):
+ * gem_export_orthomosaic: the bgr8 image of ElevationMap.cpp:87,123-125, L x L x 3 bytes row-major; a shown cell
+ *   (ix, iy) is drawn at pixel ((ix + L - start_x) % L, (iy + L - start_y) % L), everything else is black.
+ * gem_export_visual_points: the pcl::PointXYZRGB cloud of ElevationMap.cpp:112-121, one point per shown cell in
+ *   GridMapIterator order (linear index ix + iy*L): xyz (3 floats/point: grid_map cell-centre position, elevation)
+ *   and rgb (3 bytes/point).  *count_out = number of shown cells; min(count, capacity) points are written. */
+int gem_export_orthomosaic(gem_map *m, unsigned char *host_bgr);
+int gem_export_visual_points(gem_map *m, float *host_xyz, unsigned char *host_rgb, int capacity, int *count_out);
+
+/* ---- scroll-out capture into the submap store (ElevationMapping.cpp:609-765) ----
+ * gem_snapshot_shown: prevMap_ = map_.visualMap_ (:422) on the device: the shown state of this frame (after
+ *   gem_compute_features, before gem_raytracing) with its geometry; ~20 B/cell device-to-device, no host copy.
+ * gem_harvest_scrolled_out: the "L-shape" loop of :716-765 over that snapshot: every cell with traver >= 0 whose
+ *   centre lies outside the window current_xy +- length*resolution/2 on the side(s) selected by the signs of
+ *   shift_xy (both as returned by the gem_move that followed the snapshot) becomes one 32-byte PointXYZRGBICT
+ *   record {x, y, elevation, 1 | bgra, variance, intensity, traver} (:748-759; the same values GridPointData
+ *   stores, :736-737), in GridMapIterator order.  *count_out = number of such cells; min(count, capacity) written.
+ *   The host-side gate of :716 (|shift| >= resolution, init / jump flags) stays with the caller. */
+int gem_snapshot_shown(gem_map *m);
+int gem_harvest_scrolled_out(gem_map *m, const float current_xy[2], const float shift_xy[2], void *host_points32,
+                             int capacity, int *count_out);
 
 /* raw layer access (row-major L*L, float or int32 for the colour ids) for tests and
  * checkpoint/restore (the dead G_get_mapinfo/G_set_mapinfo of gpu.cu:457-475). */

@@ -94,10 +94,11 @@ struct Layers {
 class ElevationMap {
   public:
     ElevationMap(int length, float resolution, float mahalanobis_threshold = 2.5f, float obstacle_threshold = 0.7f,
-                 bool compat_box_filter = true, int device = -1, int max_points = 0)
+                 bool compat_box_filter = true, int device = -1, int max_points = 0, double grid_resolution = 0.0)
     {
         gem_config c;
         std::memset(&c, 0, sizeof c);
+        c.grid_resolution = grid_resolution; // the node's double resolution_ (ElevationMapping.hpp:314); 0 = the float
         c.length = length; c.resolution = resolution; c.mahalanobis_threshold = mahalanobis_threshold;
         c.obstacle_threshold = obstacle_threshold; c.compat_box_filter = compat_box_filter ? 1 : 0;
         c.device = device; c.max_points = max_points;
@@ -138,6 +139,37 @@ class ElevationMap {
         float *ptr[9] = {out.elevation.data(), out.variance.data(), out.rough.data(), out.slope.data(), out.traver.data(),
                          out.color_r.data(), out.color_g.data(), out.color_b.data(), out.intensity.data()};
         check(gem_export_layers(h_, ptr), "gem_export_layers");
+    }
+    // the rest of ElevationMap::show (ElevationMap.cpp:87,112-125), valid after fuse(): the bgr8 orthomosaic
+    // (length x length x 3, cv::Mat CV_8UC3 layout) and the pcl::PointXYZRGB visual cloud (xyz + rgb per shown cell)
+    void orthomosaic(std::vector<unsigned char> &bgr)
+    {
+        bgr.resize((size_t)length_ * length_ * 3);
+        check(gem_export_orthomosaic(h_, bgr.data()), "gem_export_orthomosaic");
+    }
+    int visualPoints(std::vector<float> &xyz, std::vector<unsigned char> &rgb)
+    {
+        const size_t cap = (size_t)length_ * length_;
+        xyz.resize(cap * 3);
+        rgb.resize(cap * 3);
+        int n = 0;
+        check(gem_export_visual_points(h_, xyz.data(), rgb.data(), (int)cap, &n), "gem_export_visual_points");
+        xyz.resize((size_t)n * 3);
+        rgb.resize((size_t)n * 3);
+        return n;
+    }
+    // prevMap_ = map_.visualMap_ (ElevationMapping.cpp:422) kept on the device, and the "L-shape" harvest of the
+    // cells that scrolled out of the window into the submap store (ElevationMapping.cpp:716-765).  `current` and
+    // `shift` are what move() returned for this frame; the records are PointXYZRGBICT, ready for localMap_ /
+    // visualCloud_.  The |shift| >= resolution and init/jump-flag gate of :716 stays with the caller.
+    void snapshot() { check(gem_snapshot_shown(h_), "gem_snapshot_shown"); }
+    int harvest(const float current[2], const float shift[2], std::vector<PointXYZRGBICT> &out)
+    {
+        int n = 0;
+        check(gem_harvest_scrolled_out(h_, current, shift, nullptr, 0, &n), "gem_harvest_scrolled_out");
+        out.resize((size_t)n);
+        if (n) check(gem_harvest_scrolled_out(h_, current, shift, out.data(), n, &n), "gem_harvest_scrolled_out");
+        return n;
     }
     // upstream visibilityCleanup / GEM Raytracing (gpu_process.cu:1304)
     void clean() { check(gem_raytracing(h_), "gem_raytracing"); }

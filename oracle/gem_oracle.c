@@ -803,6 +803,94 @@ void orc_closeloop(orc_map *m, const float up[2], float height_update)
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* ElevationMap::show, ElevationMap.cpp:85-149: orthomosaic + visual cloud               */
+/* ------------------------------------------------------------------------------------ */
+/* Inputs are Map_feature's output arrays, as show() receives them.  Cells are visited in GridMapIterator order
+ * (linear index i -> index_x = i % L, index_y = i / L: grid_map's column-major buffer order).
+ * The image part is plain index arithmetic (:123-125).  The point position comes from grid_map::GridMap::getPosition,
+ * an un-vendored dependency (ANYbotics/grid_map GridMapMath.cpp getPositionFromIndex, version not pinned by the
+ * reference's package.xml); ORACLE DEFINITION restating its published algorithm:
+ *   position = mapPosition + length/2 - resolution/2 - resolution * unwrappedIndex   (double), stored as float,
+ * with mapPosition / startIndex = what Move returned (ElevationMap.cpp:172-177). */
+void orc_show(const orc_map *m, double grid_res, const float *elevation, const float *traver, const int *R,
+              const int *G, const int *B, unsigned char *bgr, float *xyz, unsigned char *rgb, int *count)
+{
+    const int L = m->L;
+    /* the node's resolution_ is a double (ElevationMapping.hpp:314) and grid_map computes with it; 0 = the float */
+    const double res = grid_res > 0.0 ? grid_res : (double)m->res, half = 0.5 * ((double)L * res) - 0.5 * res;
+    int n = 0, i;
+    if (bgr) memset(bgr, 0, (size_t)L * L * 3);                      /* :87 cv::Scalar(0,0,0) */
+    for (i = 0; i < L * L; i++) {
+        const int ix = i % L, iy = i / L;
+        const int index = ix * L + iy;                                /* :99 */
+        if (elevation[index] != -10 && traver[index] != -10 && !isnan(traver[index])) { /* :101 */
+            /* :108-110 the int colour becomes a float layer value, :118-120,123-125 then an unsigned char */
+            const unsigned char r = (unsigned char)(float)R[index], g = (unsigned char)(float)G[index],
+                                b = (unsigned char)(float)B[index];
+            const int ux = (ix + L - m->start[0]) % L, uy = (iy + L - m->start[1]) % L;
+            if (bgr) {
+                unsigned char *px = bgr + 3 * ((size_t)ux * L + uy);
+                px[0] = b; px[1] = g; px[2] = r;
+            }
+            if (xyz) {
+                xyz[3 * n + 0] = (float)((double)m->centre[0] + half - res * (double)ux);
+                xyz[3 * n + 1] = (float)((double)m->centre[1] + half - res * (double)uy);
+                xyz[3 * n + 2] = elevation[index];
+            }
+            if (rgb) { rgb[3 * n + 0] = r; rgb[3 * n + 1] = g; rgb[3 * n + 2] = b; }
+            n++;
+        }
+    }
+    if (count) *count = n;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* scroll-out harvest into the submap store, ElevationMapping.cpp:716-765                */
+/* ------------------------------------------------------------------------------------ */
+/* prevMap_ is the visualMap_ of the previous frame (:422): the Map_feature outputs of that frame masked by show()
+ * (ElevationMap.cpp:101, NaN elsewhere) with that frame's centre / start index.  Every cell with
+ * elevation != -10 && traver >= 0 (:725) whose centre lies outside the CURRENT window on the side(s) selected by the
+ * signs of the last position shift (:726-733) is emitted in GridMapIterator order as one PointXYZRGBICT record
+ * {x, y, elevation, 1 | bgra, variance, intensity, traver} (:748-759; GridPointData :736-737 holds the same values).
+ * Cell-centre positions: grid_map arithmetic as in orc_show (ORACLE DEFINITION).  data[3] = 1 and a = 255 are
+ * defined here; the reference leaves them uninitialised (PointXYZRGBICT.hpp:35). */
+void orc_harvest(int L, double grid_res, const float centre_prev[2], const int start_prev[2], const float *elevation,
+                 const float *variance, const float *traver, const int *R, const int *G, const int *B,
+                 const float *intensity, const float current[2], const float shift[2], float *out, int *count)
+{
+    const double res = grid_res, half = 0.5 * ((double)L * res) - 0.5 * res;
+    const double halfwin = (double)L * res / 2;                       /* length_ * resolution_ / 2 */
+    const double lox = (double)current[0] - halfwin, hix = (double)current[0] + halfwin;
+    const double loy = (double)current[1] - halfwin, hiy = (double)current[1] + halfwin;
+    const float dx = shift[0], dy = shift[1];
+    int n = 0, i;
+    for (i = 0; i < L * L; i++) {
+        const int ix = i % L, iy = i / L, index = ix * L + iy;
+        const int shown = elevation[index] != -10 && traver[index] != -10 && !isnan(traver[index]);
+        double x, y;
+        if (!shown || !(traver[index] >= 0.0)) continue;              /* :725 on the NaN-masked layers */
+        x = (double)centre_prev[0] + half - res * (double)((ix + L - start_prev[0]) % L);
+        y = (double)centre_prev[1] + half - res * (double)((iy + L - start_prev[1]) % L);
+        if (((x < lox || y < loy) && (dx > 0 && dy > 0)) || ((x > hix || y > hiy) && (dx < 0 && dy < 0)) ||
+            ((x < lox || y > hiy) && (dx > 0 && dy < 0)) || ((x > hix || y < loy) && (dx < 0 && dy > 0)) ||
+            ((x < lox) && (dx > 0 && dy == 0)) || ((x > hix) && (dx < 0 && dy == 0)) ||
+            ((y < loy) && (dy > 0 && dx == 0)) || ((y > hiy) && (dy < 0 && dx == 0))) {
+            if (out) {
+                float *o = out + 8 * (size_t)n;
+                const unsigned r = (unsigned char)(float)R[index], g = (unsigned char)(float)G[index],
+                               b = (unsigned char)(float)B[index];
+                const unsigned bgra = b | (g << 8) | (r << 16) | 0xff000000u;
+                o[0] = (float)x; o[1] = (float)y; o[2] = elevation[index]; o[3] = 1.0f;
+                memcpy(&o[4], &bgra, 4);
+                o[5] = variance[index]; o[6] = intensity[index]; o[7] = traver[index];
+            }
+            n++;
+        }
+    }
+    if (count) *count = n;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* colourisation, ElevationMapping.cpp:331-381 (CPU loop of the ROS node)               */
 /* ------------------------------------------------------------------------------------ */
 void orc_colourise(float *xyzi, int n, const double Tc[12], const double Tl[16], const unsigned char *bgr, int width,

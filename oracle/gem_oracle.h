@@ -112,6 +112,19 @@ void orc_closeloop(orc_map *m, const float update_position[2], float height_upda
 void orc_colourise(float *xyzi, int n, const double T_camera[12], const double T_lidar[16], const unsigned char *bgr,
                    int width, int height, int row_stride, unsigned char *rgba_out);
 
+/* ElevationMap.cpp:85-149 show(): bgr8 orthomosaic (L*L*3) + visual cloud (xyz 3 floats, rgb 3 bytes per shown
+ * cell, GridMapIterator order) from Map_feature's outputs; any output may be NULL.  The cell-centre position follows
+ * grid_map's getPositionFromIndex (un-vendored, unpinned: ORACLE DEFINITION, see .c). */
+void orc_show(const orc_map *m, double grid_res /* the node's double resolution_, 0 = (double)m->res */,
+              const float *elevation, const float *traver, const int *R, const int *G, const int *B,
+              unsigned char *bgr, float *xyz, unsigned char *rgb, int *count);
+
+/* ElevationMapping.cpp:716-765: cells of the previous frame's shown map (Map_feature outputs + that frame's centre and
+ * start index) that lie outside the current window -> n x 8 floats (PointXYZRGBICT records), GridMapIterator order. */
+void orc_harvest(int L, double grid_res, const float centre_prev[2], const int start_prev[2], const float *elevation,
+                 const float *variance, const float *traver, const int *R, const int *G, const int *B,
+                 const float *intensity, const float current[2], const float shift[2], float *out, int *count);
+
 /* deterministic float trig used by the feature kernel restatement (see .c) */
 float orc_sinf(float a);
 float orc_cosf(float a);

@@ -54,13 +54,30 @@ int main()
 
     // --- facade path -----------------------------------------------------------------------
     gem_b200::Layers a;
+    std::vector<unsigned char> ortho, vis_rgb;
+    std::vector<float> vis_xyz;
+    int n_vis = 0;
     {
         gem_b200::ElevationMap map(L, res);
         map.move(pos);
         map.add(cloud.data(), cloud.size(), frame);
         map.update(0.0f);
         map.fuse(a);
+        map.orthomosaic(ortho);
+        n_vis = map.visualPoints(vis_xyz, vis_rgb);
+        map.snapshot();
         map.clean();
+        // drive 2 m along +x: the trailing rows of the snapshot leave the window and are harvested
+        const float pos2[3] = {pos[0] + 2.0f, pos[1], pos[2]};
+        float centre2[2], shift2[2];
+        int start2[2];
+        map.move(pos2, centre2, start2, shift2);
+        std::vector<gem_b200::PointXYZRGBICT> left;
+        const int n_left = map.harvest(centre2, shift2, left);
+        int bad = 0;
+        for (const auto &p : left) bad += !(p.x < centre2[0] - 0.5f * L * res) || !(p.travers >= 0.0f);
+        std::printf("harvest points=%d bad=%d shift=(%g,%g)\n", n_left, bad, shift2[0], shift2[1]);
+        if (bad || (shift2[0] > 0 && n_left == 0)) return 2;
         const gem_stats st = map.stats();
         std::printf("facade points_binned=%lld cells_touched=%lld\n", st.points_binned, st.cells_touched);
     }
@@ -99,6 +116,11 @@ int main()
             const bool shown = rm != -10.0f && tr[(size_t)sx * L + sy] != -10.0f && tr[(size_t)sx * L + sy] == tr[(size_t)sx * L + sy];
             if (shown) { valid++; if (rm != cm) mism++; } else if (cm == cm) mism++;
         }
+    // show()'s cloud has one point per shown cell, and as many pixels of the orthomosaic can be non-black
+    size_t lit = 0;
+    for (size_t p = 0; p < ortho.size(); p += 3) lit += (ortho[p] | ortho[p + 1] | ortho[p + 2]) ? 1 : 0;
+    if ((size_t)n_vis != valid || lit > valid || vis_xyz.size() != 3 * valid) mism++;
+    std::printf("visual cloud points=%d orthomosaic lit pixels=%zu\n", n_vis, lit);
     std::printf("cross-check valid=%zu mismatches=%zu\n", valid, mism);
     return mism == 0 && valid > 100 ? 0 : 1;
 }

@@ -69,6 +69,8 @@ def load():
         getattr(lib, fn).argtypes = [C.c_float]
     lib.orc_atan2f.restype = C.c_float
     lib.orc_atan2f.argtypes = [C.c_float, C.c_float]
+    lib.orc_show.argtypes = [MP, C.c_double, P, P, P, P, P, P, P, P, C.POINTER(C.c_int)]
+    lib.orc_harvest.argtypes = [C.c_int, C.c_double, P, P, P, P, P, P, P, P, P, P, P, P, C.POINTER(C.c_int)]
     lib.orc_colourise.argtypes = [P, C.c_int, P, P, P, C.c_int, C.c_int, C.c_int, P]
     lib.orc_add_points_mt.argtypes = [MP, C.c_int, P, P, P, C.c_double, C.c_double, C.POINTER(OrcSensor), P, C.c_int]
     _lib = lib
@@ -106,6 +108,7 @@ class OracleMap:
                                      float(obstacle_threshold))
         self.m.contents.compat_box_filter = 1 if compat_box_filter else 0
         self.length = int(length)
+        self.resolution = float(resolution)
         self.ncells = self.length * self.length
         self.shape = (self.length, self.length)
 
@@ -237,6 +240,36 @@ class OracleMap:
         st = C.c_int()
         g = self.lib.orc_points_to_index(self.m, float(np.float32(px)), float(np.float32(py)), C.byref(st))
         return g, st.value
+
+    def snapshot_shown(self):
+        """prevMap_ = map_.visualMap_ (ElevationMapping.cpp:422): Map_feature outputs + geometry of this frame"""
+        centre, start, _ = self.state()
+        self._prev = (self.map_feature(), np.array(centre, np.float32), np.array(start, np.int32))
+
+    def harvest_scrolled_out(self, current_xy, shift_xy, grid_res=0.0):
+        f, centre, start = self._prev
+        L = self.length
+        out = np.empty((L * L, 8), np.float32)
+        cnt = C.c_int()
+        cur = np.asarray(current_xy, np.float32)
+        sh = np.asarray(shift_xy, np.float32)
+        res = float(grid_res) if grid_res > 0 else float(np.float32(self.resolution))
+        self.lib.orc_harvest(L, res, _p(centre), _p(start), _p(f["elevation"]), _p(f["variance"]), _p(f["traver"]),
+                             _p(f["color_r"]), _p(f["color_g"]), _p(f["color_b"]), _p(f["intensity"]), _p(cur), _p(sh),
+                             _p(out), C.byref(cnt))
+        return out[:cnt.value].copy(), cnt.value
+
+    def show(self, grid_res=0.0):
+        """orthomosaic (L, L, 3) uint8 + visual cloud (xyz, rgb) of ElevationMap::show from map_feature() outputs"""
+        f = self.map_feature()
+        L = self.length
+        img = np.empty((L, L, 3), np.uint8)
+        xyz = np.empty((L * L, 3), np.float32)
+        rgb = np.empty((L * L, 3), np.uint8)
+        cnt = C.c_int()
+        self.lib.orc_show(self.m, float(grid_res), _p(f["elevation"]), _p(f["traver"]), _p(f["color_r"]), _p(f["color_g"]),
+                          _p(f["color_b"]), _p(img), _p(xyz), _p(rgb), C.byref(cnt))
+        return img, xyz[:cnt.value].copy(), rgb[:cnt.value].copy()
 
     def export_layers(self):
         """ElevationMap::show's masking + grid_map column-major layout, from the oracle state

@@ -398,6 +398,82 @@ def test_export_layers_matches_show_masking():
         assert same.all(), name
 
 
+def test_orthomosaic_and_visual_cloud_match_show():
+    """the other two products of ElevationMap::show (ElevationMap.cpp:112-125) after a scrolled multi-frame run:
+    bgr8 orthomosaic byte for byte, visual cloud point for point in GridMapIterator order"""
+    scene = synth.make_scene()
+    g, o = both(256, 0.1, compat_box_filter=False)
+    for k in range(4):
+        fr = synth.hdl64_frame(k, scene=scene, speed=9.0)
+        f = laser_frame(fr["T"])
+        for m in (g, o):
+            m.move(fr["position"])
+            m.add(fr["xyzi"], fr["rgba"], f)
+    assert tuple(o.state()[1]) != (0, 0)            # the window scrolled: start index is not trivial
+    img_o, xyz_o, rgb_o = o.show()
+    g.compute_features()
+    img_g = g.export_orthomosaic()
+    xyz_g, rgb_g, n = g.export_visual_points()
+    assert n == xyz_o.shape[0] > 5000
+    assert np.array_equal(img_g, img_o)
+    assert (img_o.reshape(-1, 3).any(axis=1)).sum() > 5000
+    assert np.array_equal(xyz_g.view(np.uint32), xyz_o.view(np.uint32))
+    assert np.array_equal(rgb_g, rgb_o)
+    # bounded capacity: the count is still the number of shown cells, the prefix is written
+    xyz_c, rgb_c, n_c = g.export_visual_points(capacity=1000)
+    assert n_c == n and xyz_c.shape[0] == 1000 and np.array_equal(xyz_c, xyz_g[:1000]) and np.array_equal(rgb_c, rgb_g[:1000])
+    # odd map size (block-edge handling: L not a multiple of 32)
+    g2, o2 = both(200, 0.1, compat_box_filter=False)
+    fr = synth.hdl64_frame(0, scene=scene)
+    for m in (g2, o2):
+        m.move(fr["position"])
+        m.add(fr["xyzi"], fr["rgba"], laser_frame(fr["T"]))
+    img_o, xyz_o, rgb_o = o2.show()
+    g2.compute_features()
+    assert np.array_equal(g2.export_orthomosaic(), img_o)
+    xyz_g, rgb_g, n = g2.export_visual_points()
+    assert n == xyz_o.shape[0] and np.array_equal(xyz_g.view(np.uint32), xyz_o.view(np.uint32)) and np.array_equal(rgb_g, rgb_o)
+
+
+def test_scroll_out_harvest_matches_node_loop():
+    """gem_snapshot_shown + gem_harvest_scrolled_out against the L-shape loop of ElevationMapping.cpp:716-765 over a
+    driving sequence (diagonal, axis-aligned and zero shifts), with the node's double resolution"""
+    scene = synth.make_scene()
+    L, res = 256, 0.1
+    g = gem_b200.ElevationMap(L, res, compat_box_filter=False, grid_resolution=0.1)
+    o = OracleMap(L, res, compat_box_filter=False)
+    steps = [(0.0, 0.0), (0.9, 0.5), (1.0, 0.0), (0.0, -0.8), (-0.7, 0.6), (0.0, 0.0), (-1.1, -0.4), (0.8, -0.9)]
+    pos = np.array([0.3, -0.2, 1.7], np.float32)
+    total = 0
+    for k, (dx, dy) in enumerate(steps):
+        fr = synth.hdl64_frame(k, scene=scene)
+        pos = pos + np.array([dx, dy, 0], np.float32)
+        T = fr["T"].copy()
+        T[:3, 3] = pos
+        f = laser_frame(T)
+        cg, sg, shg = g.move(pos)
+        co, so, sho = o.move(pos)
+        assert np.array_equal(cg, co) and np.array_equal(shg, sho)
+        if k > 0:
+            rec_g, n_g = g.harvest_scrolled_out(cg, shg)
+            rec_o, n_o = o.harvest_scrolled_out(co, sho, grid_res=0.1)
+            assert n_g == n_o, (k, n_g, n_o)
+            assert np.array_equal(rec_g.view(np.uint32), rec_o.view(np.uint32)), k
+            if dx == 0 and dy == 0:
+                assert n_g == 0
+            total += n_g
+            rec_c, n_c = g.harvest_scrolled_out(cg, shg, capacity=7)
+            assert n_c == n_g and np.array_equal(rec_c.view(np.uint32), rec_g[:7].view(np.uint32))
+        for m in (g, o):
+            m.add(fr["xyzi"], fr["rgba"], f)
+            m.compute_features()
+            m.snapshot_shown()          # prevMap_ = visualMap_ (before the ray clean-up, :421-422)
+            m.raytracing()
+    assert total > 1000
+    with pytest.raises(gem_b200.GemError):
+        gem_b200.ElevationMap(64, 0.1).harvest_scrolled_out([0, 0], [1, 0])   # no snapshot yet
+
+
 def test_opt_move_closeloop_var_update():
     c = synth.random_cloud(20000, seed=2, extent=6.0)
     f = laser_frame(np.eye(4))

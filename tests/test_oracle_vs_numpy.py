@@ -84,3 +84,80 @@ def test_raytracing_matches_python_dda():
         assert np.array_equal(bits(got), bits(want)), L
         assert (got != elev).sum() > 0           # something was cleaned
         assert (o.get_layer("lowest") == 10).all()
+
+
+def test_show_orthomosaic_and_visual_cloud_vs_numpy():
+    """orc_show against a vectorised numpy statement of ElevationMap.cpp:97-125 (+ grid_map cell-centre positions)"""
+    def laser_frame(T):
+        return gem_b200.make_frame(T, gem_b200.LaserSensorProcessor())
+    L, res = 96, 0.1
+    o = OracleMap(L, res, compat_box_filter=False)
+    for k in range(3):
+        fr = synth.hdl64_frame(k, speed=9.0)
+        o.move(fr["position"])
+        o.add(fr["xyzi"], fr["rgba"], laser_frame(fr["T"]))
+    f = o.map_feature()
+    img, xyz, rgb = o.show()
+    centre, start, _ = o.state()
+    E, T = f["elevation"].reshape(L, L), f["traver"].reshape(L, L)
+    valid = (E != -10) & (T != -10) & ~np.isnan(T)
+    ix, iy = np.nonzero(valid.T)[1], np.nonzero(valid.T)[0]          # column-major visiting order: iy outer, ix inner
+    ux, uy = (ix + L - start[0]) % L, (iy + L - start[1]) % L
+    ref_img = np.zeros((L, L, 3), np.uint8)
+    col = np.stack([f["color_b"].reshape(L, L)[ix, iy], f["color_g"].reshape(L, L)[ix, iy], f["color_r"].reshape(L, L)[ix, iy]], axis=1)
+    ref_img[ux, uy] = col.astype(np.uint8)
+    assert valid.sum() > 500 and np.array_equal(img, ref_img)
+    half = 0.5 * L * np.float64(np.float32(res)) - 0.5 * np.float64(np.float32(res))
+    px = (np.float64(centre[0]) + half - np.float64(np.float32(res)) * ux).astype(np.float32)
+    py = (np.float64(centre[1]) + half - np.float64(np.float32(res)) * uy).astype(np.float32)
+    assert np.array_equal(xyz[:, 0], px) and np.array_equal(xyz[:, 1], py) and np.array_equal(xyz[:, 2], E[ix, iy])
+    assert np.array_equal(rgb, col[:, ::-1].astype(np.uint8))
+
+
+def test_harvest_scrolled_out_vs_numpy():
+    """orc_harvest (ElevationMapping.cpp:716-765) against a vectorised numpy statement, all eight direction cases"""
+    L, res = 96, 0.1
+    def laser_frame(T):
+        return gem_b200.make_frame(T, gem_b200.LaserSensorProcessor())
+    o = OracleMap(L, res, compat_box_filter=False)
+    fr = synth.hdl64_frame(0)
+    o.move(fr["position"])
+    o.add(fr["xyzi"], fr["rgba"], laser_frame(fr["T"]))
+    o.snapshot_shown()
+    f, centre_p, start_p = o._prev
+    p0 = np.array(fr["position"], np.float32)
+    total = 0
+    for dx, dy in [(0.7, 0.4), (-0.7, -0.4), (0.7, -0.4), (-0.7, 0.4), (0.5, 0.0), (-0.5, 0.0), (0.0, 0.5), (0.0, -0.5), (0.0, 0.0)]:
+        o2 = OracleMap(L, res, compat_box_filter=False)
+        o2.move(p0)
+        cur, _, shift = o2.move(p0 + np.array([dx, dy, 0], np.float32))
+        for grid_res in (0.0, 0.1):                       # float-derived and the node's double resolution
+            rec, n = o.harvest_scrolled_out(cur, shift, grid_res=grid_res)
+            r = np.float64(np.float32(res)) if grid_res == 0 else np.float64(grid_res)
+            E, T = f["elevation"].reshape(L, L), f["traver"].reshape(L, L)
+            shown = (E != -10) & (T != -10) & ~np.isnan(T) & (T >= 0)
+            iy, ix = np.nonzero(shown.T)
+            half = 0.5 * (L * r) - 0.5 * r
+            x = np.float64(centre_p[0]) + half - r * ((ix + L - start_p[0]) % L)
+            y = np.float64(centre_p[1]) + half - r * ((iy + L - start_p[1]) % L)
+            hw = L * r / 2
+            lox, hix, loy, hiy = cur[0] - hw, cur[0] + hw, cur[1] - hw, cur[1] + hw
+            sx, sy = shift
+            out = (((x < lox) | (y < loy)) & (sx > 0 and sy > 0)) | (((x > hix) | (y > hiy)) & (sx < 0 and sy < 0)) | \
+                  (((x < lox) | (y > hiy)) & (sx > 0 and sy < 0)) | (((x > hix) | (y < loy)) & (sx < 0 and sy > 0)) | \
+                  ((x < lox) & (sx > 0 and sy == 0)) | ((x > hix) & (sx < 0 and sy == 0)) | \
+                  ((y < loy) & (sy > 0 and sx == 0)) | ((y > hiy) & (sy < 0 and sx == 0))
+            ix, iy, x, y = ix[out], iy[out], x[out], y[out]
+            assert n == ix.size
+            if dx == 0 and dy == 0:
+                assert n == 0
+            assert np.array_equal(rec[:, 0], x.astype(np.float32)) and np.array_equal(rec[:, 1], y.astype(np.float32))
+            assert np.array_equal(rec[:, 2], E[ix, iy]) and np.all(rec[:, 3] == 1)
+            assert np.array_equal(rec[:, 5], f["variance"].reshape(L, L)[ix, iy])
+            assert np.array_equal(bits(rec[:, 6]), bits(f["intensity"].reshape(L, L)[ix, iy]))
+            assert np.array_equal(rec[:, 7], T[ix, iy])
+            bgra = rec[:, 4].copy().view(np.uint32)
+            assert np.array_equal(bgra & 255, f["color_b"].reshape(L, L)[ix, iy] & 255)
+            assert np.array_equal((bgra >> 16) & 255, f["color_r"].reshape(L, L)[ix, iy] & 255)
+            total += n
+    assert total > 500
