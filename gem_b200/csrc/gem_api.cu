@@ -48,6 +48,7 @@ struct gem_map {
     int ctr_cur = 0;          // which counter buffer the NEXT call uses (it is zero)
     Counters *ctr_last = nullptr; // counters of the last finished call
     bool pdl = false;         // programmatic dependent launch between the add-path kernels (opt-in)
+    bool pdl_front = false;   // stream mode only: PDL between transform -> alloc -> scatter on the front stream (opt-in)
     int coop_blocks = 0;      // co-resident grid size of the fused kernel (0 = unavailable)
     int fused_max_points = 1 << 20;
     // staging (device), lazily allocated
@@ -178,6 +179,9 @@ template <typename T> int dev_alloc(gem_map *m, T **p, size_t count)
     return GEM_OK;
 }
 
+// capacity of a per-call list of the cells holding MORE than k of a call's <= P records: at most P / (k + 1) such
+// cells exist, and never more than the map has
+inline size_t list_cap(size_t P, size_t nc, int k) { return std::min(nc, P / (size_t)(k + 1)) + 1; }
 inline int blocks_for(size_t n, int bs, int cap = 148 * 16)
 {
     size_t b = (n + bs - 1) / bs;
@@ -431,14 +435,14 @@ static GridMapFrame grid_frame(const gem_map *m, float cx, float cy, int sx, int
 // count -> scan -> write of the cells Src takes, in GridMapIterator order; returns the total through *total_out
 template <class Src> static int compact_cells(gem_map *m, const Src &src, int capacity, int *total_out)
 {
-    const int L = m->L;
+    const int L = m->L, nch = (L + 31) / 32;
     int rc;
-    if (!m->d_viscnt) { if ((rc = dev_alloc(m, &m->d_viscnt, (size_t)L * VIS_WARPS + 1))) return rc; }
-    int *d_total = m->d_viscnt + (size_t)L * VIS_WARPS;
-    const int blocks = (L + 31) / 32;
-    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_count<Src><<<blocks, 1024, 0, m->stream>>>(src, L, m->d_viscnt));
-    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_scan<<<1, 1024, 0, m->stream>>>(m->d_viscnt, L * VIS_WARPS, d_total));
-    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_write<Src><<<blocks, 1024, 0, m->stream>>>(src, L, m->d_viscnt, capacity));
+    if (!m->d_viscnt) { if ((rc = dev_alloc(m, &m->d_viscnt, (size_t)L * nch + 1))) return rc; }
+    int *d_total = m->d_viscnt + (size_t)L * nch;
+    const dim3 grid(nch, nch);
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_count<Src><<<grid, 1024, 0, m->stream>>>(src, L, nch, m->d_viscnt));
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_scan<<<1, 1024, 0, m->stream>>>(m->d_viscnt, L * nch, d_total));
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_write<Src><<<grid, 1024, 0, m->stream>>>(src, L, nch, m->d_viscnt, capacity));
     GEM_CUDA(m, cudaGetLastError());
     GEM_CUDA(m, cudaMemcpyAsync(total_out, d_total, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     GEM_CUDA(m, cudaStreamSynchronize(m->stream));
@@ -526,7 +530,7 @@ int gem_create(const gem_config *cfg, gem_map **out)
         (rc = dev_alloc(m, &m->ml.traver_out, nc)) || (rc = dev_alloc(m, &m->sc.cnt, nc)) ||
         (rc = dev_alloc(m, &m->sc.cellBase, nc)) || (rc = dev_alloc(m, &m->sc.touched, P < nc ? P : nc)) ||
         (rc = dev_alloc(m, &m->ctr_buf[0], 2)) || (rc = dev_alloc(m, &m->sc.key, P)) ||
-        (rc = dev_alloc(m, &m->sc.tsmall, P < nc ? P : nc)) || (rc = dev_alloc(m, &m->sc.tlarge, (P < nc ? P : nc) / FOLD_SMALL_K + 1)) ||
+        (rc = dev_alloc(m, &m->sc.tsmall, P < nc ? P : nc)) || (rc = dev_alloc(m, &m->sc.tlarge, list_cap(P, nc, FOLD_SMALL_K))) || (rc = dev_alloc(m, &m->sc.tlong, list_cap(P, nc, FOLD_LONG_K))) ||
         (rc = dev_alloc(m, &m->sc.rank, P)) || (rc = dev_alloc(m, &m->sc.h, P)) ||
         (rc = dev_alloc(m, &m->sc.hv, P)) || (rc = dev_alloc(m, &m->sc.recA, P)) ||
         (rc = dev_alloc(m, &m->sc.recI, P)))
@@ -563,6 +567,8 @@ int gem_create(const gem_config *cfg, gem_map **out)
         // CTAs occupy the SMs the predecessor's serial fold tail needs), so it is opt-in
         const char *envp = getenv("GEM_B200_PDL");
         if (envp && atoi(envp) == 1) m->pdl = true;
+        const char *envf = getenv("GEM_B200_PDL_FRONT");
+        if (envf && atoi(envf) == 1) m->pdl_front = true;
         const char *envn = getenv("GEM_B200_FUSED_MAX_POINTS");
         if (envn && atoi(envn) > 0) m->fused_max_points = atoi(envn);
         cudaGetLastError();
@@ -768,7 +774,7 @@ static int pipe_setup(gem_map *m)
         Scratch &sc = m->pipe_sc[i];
         memset(&sc, 0, sizeof sc);
         if ((rc = dev_alloc(m, &sc.cnt, nc)) || (rc = dev_alloc(m, &sc.cellBase, nc)) || (rc = dev_alloc(m, &sc.touched, T)) ||
-            (rc = dev_alloc(m, &sc.tsmall, T)) || (rc = dev_alloc(m, &sc.tlarge, T / FOLD_SMALL_K + 1)) ||
+            (rc = dev_alloc(m, &sc.tsmall, T)) || (rc = dev_alloc(m, &sc.tlarge, list_cap(P, nc, FOLD_SMALL_K))) || (rc = dev_alloc(m, &sc.tlong, list_cap(P, nc, FOLD_LONG_K))) ||
             (rc = dev_alloc(m, &sc.key, P)) || (rc = dev_alloc(m, &sc.rank, P)) || (rc = dev_alloc(m, &sc.h, P)) ||
             (rc = dev_alloc(m, &sc.hv, P)) || (rc = dev_alloc(m, &sc.recA, P)) || (rc = dev_alloc(m, &sc.recI, P)))
             return rc;
@@ -814,9 +820,10 @@ int gem_add_points_stream(gem_map *m, const void *xyzi, const void *rgba, int n,
     const int pb = blocks_for((size_t)n, ADD_BLOCK, 148 * 16);
     GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_TRANSFORM_BIN,
                   k_transform_bin<IN_XYZI><<<pb, ADD_BLOCK, 0, m->front_stream>>>(m->geom, m->ml, fp, in, n, sc, none, pb, nullptr, nullptr));
-    GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_ALLOC, k_alloc_cells<<<blocks_for((size_t)n, ADD_BLOCK, 148 * 4), ADD_BLOCK, 0, m->front_stream>>>(sc));
+    GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_ALLOC,
+                  launch_pdl(m->pdl_front, k_alloc_cells, blocks_for((size_t)n, ADD_BLOCK, 148 * 4), ADD_BLOCK, m->front_stream, sc));
     GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_SCATTER,
-                  k_scatter<ATTR_XYZI><<<blocks_for((size_t)n, ADD_BLOCK, 148 * 16), ADD_BLOCK, 0, m->front_stream>>>(a, n, sc));
+                  launch_pdl(m->pdl_front, k_scatter<ATTR_XYZI, 1>, blocks_for((size_t)n, ADD_BLOCK, 148 * 16), ADD_BLOCK, m->front_stream, a, n, sc));
     GEM_CUDA(m, cudaEventRecord(m->ev_front[par], m->front_stream));
     // main stream: deferred scroll clears / floors, then the fold (the only kernel that touches the layers)
     if (!m->pending.empty() && (rc = flush_all_pending(m))) return rc;
@@ -1207,7 +1214,7 @@ int gem_export_orthomosaic(gem_map *m, unsigned char *host_bgr)
     if (rc) return rc;
     if ((rc = flush_for_observer(m))) return rc;
     unsigned char *d_img = reinterpret_cast<unsigned char *>(m->d_out);
-    GEM_LAUNCH(m, GEM_PROF_OTHER, k_orthomosaic<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, d_img));
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_orthomosaic<<<blocks_for((m->nc + 3) / 4, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, d_img));
     GEM_CUDA(m, cudaGetLastError());
     GEM_CUDA(m, cudaMemcpyAsync(host_bgr, d_img, m->nc * 3, cudaMemcpyDeviceToHost, m->stream));
     GEM_CUDA(m, cudaStreamSynchronize(m->stream));

@@ -82,6 +82,20 @@ def test_order_dependence_dense_collisions():
     assert g.stats()["max_points_per_cell"] > 20
 
 
+def test_every_cell_carries_a_long_list():
+    """small map, every cell gets tens of points: the per-call lists of long cells (work queue of k_fold) are as
+    long as the map has cells; their capacity is min(cells, points / (k + 1)), not cells / k"""
+    L, res = 96, 0.1
+    c = synth.random_cloud(500000, seed=21, extent=4.9, zmin=-0.5, zmax=1.0, dup_frac=0.0)
+    f = laser_frame(np.eye(4), base_z=0.0)
+    g, o = both(L, res, compat_box_filter=False)
+    for m in (g, o):
+        m.add(c["xyzi"], c["rgba"], f)
+    assert_layers_equal(g, o, what="all cells long")
+    st = g.stats()
+    assert st["cells_touched"] > 0.9 * L * L and st["max_points_per_cell"] > 60
+
+
 def test_very_long_cell_lists_fallback_paths():
     """> 1024 points in one cell exercises the global-memory selection path of k_fold"""
     L, res = 32, 0.5
