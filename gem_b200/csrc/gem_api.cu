@@ -74,10 +74,14 @@ struct gem_map {
     unsigned async_calls = 0;
     // gem_add_points_stream: frame-pipelined mode (own scratch sets, front stream, events)
     bool pipe_ready = false;
-    Scratch pipe_sc[2];
-    Counters *pipe_ctr[3] = {nullptr, nullptr, nullptr};
-    cudaStream_t front_stream = nullptr;
-    cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_fold[2] = {nullptr, nullptr};
+    // frame pipeline of gem_add_points_stream: three stages on three streams (transform+bin | alloc+scatter | fold),
+    // three scratch sets (one per frame in flight), four counter buffers (the transform kernel of frame i clears
+    // the buffer of frame i+1, last used by frame i-3)
+    Scratch pipe_sc[3];
+    Counters *pipe_ctr[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t front_stream = nullptr, mid_stream = nullptr;
+    bool mid_owned = false;
+    cudaEvent_t ev_bin[3] = {nullptr, nullptr, nullptr}, ev_front[3] = {nullptr, nullptr, nullptr}, ev_fold[3] = {nullptr, nullptr, nullptr};
     unsigned pipe_calls = 0;
     // gem_add_points_multi: ring of per-call FrameParams tables (pinned host + device)
     FrameParams *h_frames = nullptr, *d_frames = nullptr;
@@ -588,11 +592,13 @@ int gem_destroy(gem_map *m)
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     if (m->h_ctr_ring) cudaFreeHost(m->h_ctr_ring);
     if (m->h_frames) cudaFreeHost(m->h_frames);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
+        if (m->ev_bin[i]) cudaEventDestroy(m->ev_bin[i]);
         if (m->ev_front[i]) cudaEventDestroy(m->ev_front[i]);
         if (m->ev_fold[i]) cudaEventDestroy(m->ev_fold[i]);
     }
     if (m->front_stream) { cudaStreamSynchronize(m->front_stream); cudaStreamDestroy(m->front_stream); }
+    if (m->mid_owned && m->mid_stream) { cudaStreamSynchronize(m->mid_stream); cudaStreamDestroy(m->mid_stream); }
     for (int i = 0; i < 4; i++) if (m->ev_frames[i]) cudaEventDestroy(m->ev_frames[i]);
     for (int i = 0; i < 2; i++) {
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
@@ -770,7 +776,7 @@ static int pipe_setup(gem_map *m)
     if (m->pipe_ready) return GEM_OK;
     int rc;
     const size_t nc = m->nc, P = (size_t)m->P, T = P < nc ? P : nc;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
         Scratch &sc = m->pipe_sc[i];
         memset(&sc, 0, sizeof sc);
         if ((rc = dev_alloc(m, &sc.cnt, nc)) || (rc = dev_alloc(m, &sc.cellBase, nc)) || (rc = dev_alloc(m, &sc.touched, T)) ||
@@ -779,15 +785,23 @@ static int pipe_setup(gem_map *m)
             (rc = dev_alloc(m, &sc.hv, P)) || (rc = dev_alloc(m, &sc.recA, P)) || (rc = dev_alloc(m, &sc.recI, P)))
             return rc;
         GEM_CUDA(m, cudaMemsetAsync(sc.cnt, 0, nc * sizeof(int), m->stream));
+        GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_bin[i], cudaEventDisableTiming));
         GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_front[i], cudaEventDisableTiming));
         GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_fold[i], cudaEventDisableTiming));
     }
-    if ((rc = dev_alloc(m, &m->pipe_ctr[0], 3))) return rc;
-    m->pipe_ctr[1] = m->pipe_ctr[0] + 1;
-    m->pipe_ctr[2] = m->pipe_ctr[0] + 2;
-    GEM_CUDA(m, cudaMemsetAsync(m->pipe_ctr[0], 0, 3 * sizeof(Counters), m->stream));
+    if ((rc = dev_alloc(m, &m->pipe_ctr[0], 4))) return rc;
+    for (int i = 1; i < 4; i++) m->pipe_ctr[i] = m->pipe_ctr[0] + i;
+    GEM_CUDA(m, cudaMemsetAsync(m->pipe_ctr[0], 0, 4 * sizeof(Counters), m->stream));
     GEM_CUDA(m, cudaStreamCreateWithFlags(&m->front_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) GEM_CUDA(m, cudaEventRecord(m->ev_fold[i], m->stream)); // sets are free once init is done
+    {   // GEM_B200_STREAM_STAGES=2 keeps alloc+scatter on the transform stream (the two-stage pipeline)
+        const char *env = getenv("GEM_B200_STREAM_STAGES");
+        if (env && atoi(env) == 2) m->mid_stream = m->front_stream;
+        else {
+            GEM_CUDA(m, cudaStreamCreateWithFlags(&m->mid_stream, cudaStreamNonBlocking));
+            m->mid_owned = true;
+        }
+    }
+    for (int i = 0; i < 3; i++) GEM_CUDA(m, cudaEventRecord(m->ev_fold[i], m->stream)); // sets are free once init is done
     m->pipe_ready = true;
     return GEM_OK;
 }
@@ -801,10 +815,10 @@ int gem_add_points_stream(gem_map *m, const void *xyzi, const void *rgba, int n,
     if (rc) return rc;
     if (n == 0) return flush_all_pending(m);
     const unsigned i = m->pipe_calls++;
-    const int par = (int)(i & 1u), c = (int)(i % 3u);
+    const int par = (int)(i % 3u), c = (int)(i & 3u);
     Scratch sc = m->pipe_sc[par];
     sc.ctr = m->pipe_ctr[c];
-    sc.ctr_next = m->pipe_ctr[(c + 1) % 3];
+    sc.ctr_next = m->pipe_ctr[(c + 1) & 3];
     sc.tstamp = nullptr;
     const FrameParams fp = make_frame(frame);
     PointInput in{};
@@ -813,19 +827,24 @@ int gem_add_points_stream(gem_map *m, const void *xyzi, const void *rgba, int n,
     AttrInput a{};
     a.xyzi = in.xyzi;
     a.rgba = in.rgba;
-    // front stream: transform+bin, alloc, scatter of THIS frame -- may overlap the fold of the previous
-    // frame; it only waits for the fold that last used this scratch set (two calls ago)
+    // stage 1 (front stream): transform+bin of THIS frame -- overlaps alloc+scatter of the previous frame and the
+    // fold of the one before; it only waits for the fold that last used this scratch set (three calls ago)
     GEM_CUDA(m, cudaStreamWaitEvent(m->front_stream, m->ev_fold[par], 0));
     RegionOps none{};
     const int pb = blocks_for((size_t)n, ADD_BLOCK, 148 * 16);
     GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_TRANSFORM_BIN,
                   k_transform_bin<IN_XYZI><<<pb, ADD_BLOCK, 0, m->front_stream>>>(m->geom, m->ml, fp, in, n, sc, none, pb, nullptr, nullptr));
-    GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_ALLOC,
-                  launch_pdl(m->pdl_front, k_alloc_cells, blocks_for((size_t)n, ADD_BLOCK, 148 * 4), ADD_BLOCK, m->front_stream, sc));
-    GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_SCATTER,
-                  launch_pdl(m->pdl_front, k_scatter<ATTR_XYZI, 1>, blocks_for((size_t)n, ADD_BLOCK, 148 * 16), ADD_BLOCK, m->front_stream, a, n, sc));
-    GEM_CUDA(m, cudaEventRecord(m->ev_front[par], m->front_stream));
-    // main stream: deferred scroll clears / floors, then the fold (the only kernel that touches the layers)
+    // stage 2 (mid stream): alloc + scatter
+    if (m->mid_stream != m->front_stream) {
+        GEM_CUDA(m, cudaEventRecord(m->ev_bin[par], m->front_stream));
+        GEM_CUDA(m, cudaStreamWaitEvent(m->mid_stream, m->ev_bin[par], 0));
+    }
+    GEM_LAUNCH_ON(m, m->mid_stream, GEM_PROF_ALLOC,
+                  launch_pdl(m->pdl_front, k_alloc_cells, blocks_for((size_t)n, ADD_BLOCK, 148 * 4), ADD_BLOCK, m->mid_stream, sc));
+    GEM_LAUNCH_ON(m, m->mid_stream, GEM_PROF_SCATTER,
+                  launch_pdl(m->pdl_front, k_scatter<ATTR_XYZI, 1>, blocks_for((size_t)n, ADD_BLOCK, 148 * 16), ADD_BLOCK, m->mid_stream, a, n, sc));
+    GEM_CUDA(m, cudaEventRecord(m->ev_front[par], m->mid_stream));
+    // stage 3 (main stream): deferred scroll clears / floors, then the fold (the only kernel that touches the layers)
     if (!m->pending.empty() && (rc = flush_all_pending(m))) return rc;
     GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_front[par], 0));
     GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<blocks_for((size_t)n, ADD_BLOCK, 148 * 8), ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, sc, 1, 1));
