@@ -216,8 +216,9 @@ class TiledElevationMap:
             own = torch.empty((rows, cols), dtype=torch.float32, device=self.dev)
             self.map.get_layer_device("elevation", own)
             mine = border_pack(own)
-            allb = torch.empty((self.world, mine.numel()), dtype=torch.float32, device=self.dev)
-            dist.all_gather_into_tensor(allb, mine)
+            flat = torch.empty(self.world * mine.numel(), dtype=torch.float32, device=self.dev)
+            dist.all_gather_into_tensor(flat, mine)          # flat output: accepted by NCCL and gloo alike
+            allb = flat.view(self.world, mine.numel())
             padded = padded_from_borders(own, allb, self.rank, self.world).contiguous()
             self.map.compute_features_tiled(padded)
             self._keep_feat = (own, allb, padded)
@@ -231,8 +232,9 @@ class TiledElevationMap:
         with torch.cuda.stream(self.stream):
             own = torch.empty((rows, cols), dtype=torch.float32, device=self.dev)
             self.map.get_layer_device("lowest", own)
-            allt = torch.empty((self.world, rows, cols), dtype=torch.float32, device=self.dev)
-            dist.all_gather_into_tensor(allt, own)
+            flat = torch.empty(self.world * rows * cols, dtype=torch.float32, device=self.dev)
+            dist.all_gather_into_tensor(flat, own.view(-1))
+            allt = flat.view(self.world, rows, cols)
             glob = global_from_tiles(list(allt), self.world, self.L)
             self.map.raytracing_tiled(glob)
 

@@ -90,3 +90,32 @@ def test_halo_assembly_matches_slicing(world):
     for r in range(world):
         r0, nr, c0, nc = tiled.tile_of_rank(r, world, L)
         assert torch.equal(tiled.padded_from_borders(tiles[r], borders, r, world), gp[r0:r0 + nr + 4, c0:c0 + nc + 4])
+
+
+def _halo_worker(rank, world, port):
+    """the collective part of TiledElevationMap.compute_features / clean: all_gather of the border strips and of the
+    lowest tiles, then local assembly -- with gloo on CPU tensors"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L = 32
+    g = (torch.arange(L * L, dtype=torch.float32).view(L, L) * 0.5 - 100.0)
+    r0, nr, c0, nc = tiled.tile_of_rank(rank, world, L)
+    own = g[r0:r0 + nr, c0:c0 + nc].contiguous()
+    mine = tiled.border_pack(own)
+    flat = torch.empty(world * mine.numel(), dtype=torch.float32)
+    dist.all_gather_into_tensor(flat, mine)
+    padded = tiled.padded_from_borders(own, flat.view(world, mine.numel()), rank, world)
+    gp = torch.full((L + 4, L + 4), -10.0)
+    gp[2:-2, 2:-2] = g
+    assert torch.equal(padded, gp[r0:r0 + nr + 4, c0:c0 + nc + 4])
+    flat = torch.empty(world * nr * nc, dtype=torch.float32)
+    dist.all_gather_into_tensor(flat, own.view(-1))
+    assert torch.equal(tiled.global_from_tiles(list(flat.view(world, nr, nc)), world, L), g)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_halo_and_lowest_gather_gloo_world2():
+    port = 29820 + os.getpid() % 150
+    mp.spawn(_halo_worker, args=(2, port), nprocs=2, join=True)
