@@ -441,12 +441,13 @@ template <class Src> static int compact_cells(gem_map *m, const Src &src, int ca
 {
     const int L = m->L, nch = (L + 31) / 32;
     int rc;
-    if (!m->d_viscnt) { if ((rc = dev_alloc(m, &m->d_viscnt, (size_t)L * nch + 1))) return rc; }
-    int *d_total = m->d_viscnt + (size_t)L * nch;
+    const int n = L * nch, nseg = (n + SCAN_SEG - 1) / SCAN_SEG;
+    if (!m->d_viscnt) { if ((rc = dev_alloc(m, &m->d_viscnt, (size_t)n + nseg + 1))) return rc; }
+    int *d_segtot = m->d_viscnt + n, *d_total = d_segtot + nseg;
     const dim3 grid(nch, nch);
     GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_count<Src><<<grid, 1024, 0, m->stream>>>(src, L, nch, m->d_viscnt));
-    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_scan<<<1, 1024, 0, m->stream>>>(m->d_viscnt, L * nch, d_total));
-    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_write<Src><<<grid, 1024, 0, m->stream>>>(src, L, nch, m->d_viscnt, capacity));
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_scan<<<nseg, SCAN_SEG, 0, m->stream>>>(m->d_viscnt, n, d_segtot));
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_write<Src><<<grid, 1024, 0, m->stream>>>(src, L, nch, m->d_viscnt, d_segtot, nseg, d_total, capacity));
     GEM_CUDA(m, cudaGetLastError());
     GEM_CUDA(m, cudaMemcpyAsync(total_out, d_total, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     GEM_CUDA(m, cudaStreamSynchronize(m->stream));
