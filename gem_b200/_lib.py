@@ -36,6 +36,7 @@ class GemSensorModel(C.Structure):
         ("type", C.c_int), ("min_radius", C.c_float), ("beam_angle", C.c_float), ("beam_constant", C.c_float),
         ("normal_factor_a", C.c_double), ("normal_factor_b", C.c_double), ("normal_factor_c", C.c_double),
         ("normal_factor_d", C.c_double), ("normal_factor_e", C.c_double), ("lateral_factor", C.c_double),
+        ("cutoff_min_depth", C.c_double), ("cutoff_max_depth", C.c_double),
     ]
 
 

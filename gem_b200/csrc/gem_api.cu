@@ -225,6 +225,8 @@ FrameParams make_frame(const gem_frame *f)
     p.nf_d = f->sensor.normal_factor_d;
     p.nf_e = f->sensor.normal_factor_e;
     p.lat = f->sensor.lateral_factor;
+    p.cut_lo = (float)f->sensor.cutoff_min_depth; // pcl::PassThrough::setFilterLimits takes floats
+    p.cut_hi = (float)f->sensor.cutoff_max_depth;
     return p;
 }
 

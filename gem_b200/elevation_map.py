@@ -33,7 +33,7 @@ class LaserSensorProcessor:
 
     def model(self) -> GemSensorModel:
         return GemSensorModel(_lib.SENSOR_LASER, self.min_radius, self.beam_angle, self.beam_constant,
-                              0.0, 0.0, 0.0, 0.0, 1.0, 0.0)
+                              0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0)
 
 
 @dataclass
@@ -54,7 +54,7 @@ class StructuredLightSensorProcessor:
     def model(self) -> GemSensorModel:
         return GemSensorModel(_lib.SENSOR_STRUCTURED_LIGHT, 0.0, 0.0, 0.0, self.normal_factor_a,
                               self.normal_factor_b, self.normal_factor_c, self.normal_factor_d,
-                              self.normal_factor_e, self.lateral_factor)
+                              self.normal_factor_e, self.lateral_factor, self.cutoff_min_depth, self.cutoff_max_depth)
 
 
 def make_frame(T, sensor, base_z: float = 0.0, rotation_variance=None, C_SB_transpose=None,

@@ -117,7 +117,7 @@ def d435_pose(frame: int, speed: float = 0.5, rate_hz: float = 30.0, height: flo
     return T, np.array([x, 0.0, height])
 
 
-def d435_frame(frame: int = 0, scene=None):
+def d435_frame(frame: int = 0, scene=None, raw: bool = True):
     if scene is None:
         scene = make_scene(SCENE_SEED + 7, n_boxes=60, extent=6.0)
     rng = np.random.Generator(np.random.PCG64(FRAME_SEED0 + 100000 + frame))
@@ -130,9 +130,16 @@ def d435_frame(frame: int = 0, scene=None):
     nrm = np.linalg.norm(d_w, axis=1)
     t, _ = _cast(T[:3, 3], d_w / nrm[:, None], scene, 0.0, 50.0)
     depth = t / nrm  # z in the optical frame
-    ok = np.isfinite(depth) & (depth >= 0.2) & (depth <= 3.25)
-    p_s = d_s[ok] * depth[ok, None]
+    # the full 640x480 image as the camera driver publishes it: pixels without a return carry NaN, returns
+    # beyond the useful range keep their depth; dropping them is cleanPointCloud's job
+    # (StructuredLightSensorProcessor.cpp:51-66), i.e. part of the path under test
+    hit = np.isfinite(depth) & (depth <= 8.0)
+    dd = np.where(hit, depth, np.nan)
+    p_s = d_s * dd[:, None]
     p_s[:, 2] += rng.uniform(-0.002, 0.002, p_s.shape[0])
+    if not raw:
+        keep = np.isfinite(dd) & (dd >= 0.2) & (dd <= 3.25)
+        p_s = p_s[keep]
     n = p_s.shape[0]
     inten = rng.integers(1, 256, n).astype(np.float32)
     rgba = rng.integers(1, 256, (n, 4)).astype(np.uint8)

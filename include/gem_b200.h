@@ -68,12 +68,21 @@ typedef struct gem_config {
 enum { GEM_SENSOR_LASER = 0, GEM_SENSOR_STRUCTURED_LIGHT = 1 };
 
 /* Sensor noise model: laser = gpu.cu:410-411 (C_min_r, C_beam_a, C_beam_c);
- * structured light = StructuredLightSensorProcessor.cpp:129-139 (doubles). */
+ * structured light = StructuredLightSensorProcessor.cpp:129-139 (doubles), plus the depth
+ * pass-through of its cleanPointCloud (:51-66). */
 typedef struct gem_sensor_model {
     int type;
     float min_radius, beam_angle, beam_constant;
     double normal_factor_a, normal_factor_b, normal_factor_c, normal_factor_d, normal_factor_e;
     double lateral_factor;
+    /* structured light only: cleanPointCloud's pcl::PassThrough on the sensor-frame z
+     * (StructuredLightSensorProcessor.cpp:51-66, realsense_d435.yaml 0.2 / 3.25; the node's defaults are
+     * DBL_MIN / DBL_MAX, :39-40).  PCL converts the limits to float and drops a point when it is not finite or
+     * z < min || z > max.  Always applied for GEM_SENSOR_STRUCTURED_LIGHT by the fused add calls (a dropped point
+     * is a rejected point: the order of the remaining ones is unchanged); ignored for the laser model, whose
+     * cleanPointCloud only removes non-finite points (LaserSensorProcessor.cpp:50-59) -- those never pass the
+     * height window of gpu.cu:397 anyway. */
+    double cutoff_min_depth, cutoff_max_depth;
 } gem_sensor_model;
 
 /* Per-frame constants = the by-value arguments of Process_points (gpu.cu:1085), derived by

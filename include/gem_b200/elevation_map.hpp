@@ -48,6 +48,7 @@ struct LaserSensorProcessor { // LaserSensorProcessor.cpp:38-47
 struct StructuredLightSensorProcessor { // StructuredLightSensorProcessor.cpp:36-48
     double normal_factor_a = 0.000611, normal_factor_b = 0.003587, normal_factor_c = 0.3515;
     double normal_factor_d = 0.0, normal_factor_e = 1.0, lateral_factor = 0.01576;
+    double cutoff_min_depth = 0.2, cutoff_max_depth = 3.25; // cleanPointCloud pass-through, :51-66
     double ignore_points_above = std::numeric_limits<double>::infinity();
     double ignore_points_below = -std::numeric_limits<double>::infinity();
     gem_sensor_model model() const
@@ -56,6 +57,7 @@ struct StructuredLightSensorProcessor { // StructuredLightSensorProcessor.cpp:36
         m.type = GEM_SENSOR_STRUCTURED_LIGHT;
         m.normal_factor_a = normal_factor_a; m.normal_factor_b = normal_factor_b; m.normal_factor_c = normal_factor_c;
         m.normal_factor_d = normal_factor_d; m.normal_factor_e = normal_factor_e; m.lateral_factor = lateral_factor;
+        m.cutoff_min_depth = cutoff_min_depth; m.cutoff_max_depth = cutoff_max_depth;
         return m;
     }
 };

@@ -357,6 +357,23 @@ static float sensor_variances(const orc_sensor *s, float x, float y, float z, fl
     }
 }
 
+int orc_clean_point_cloud(const orc_sensor *s, int n, float *xyzi, unsigned char *rgba)
+{
+    int i, k = 0;
+    float lo = (float)s->cutoff_min, hi = (float)s->cutoff_max; /* setFilterLimits(const float&, const float&) */
+    for (i = 0; i < n; i++) {
+        const float x = xyzi[4 * i], y = xyzi[4 * i + 1], z = xyzi[4 * i + 2];
+        if (!isfinite(x) || !isfinite(y) || !isfinite(z)) continue; /* both filters */
+        if (s->type == ORC_SENSOR_STRUCTURED_LIGHT && (z < lo || z > hi)) continue; /* SL.cpp:58 */
+        if (k != i) {
+            memcpy(xyzi + 4 * k, xyzi + 4 * i, 4 * sizeof(float));
+            if (rgba) memcpy(rgba + 4 * k, rgba + 4 * i, 4);
+        }
+        k++;
+    }
+    return k;
+}
+
 static void process_one(const orc_map *m, float x, float y, float z, const float T[16],
                         double relLower, double relUpper, const orc_sensor *sensor,
                         const float sJ[3], const float rotVar[9], const float C_SB_T[9],

@@ -58,7 +58,19 @@ typedef struct orc_sensor {
     float min_r, beam_a, beam_c;
     /* structured light (SL.cpp:129-141), parameters are double in the reference */
     double nf_a, nf_b, nf_c, nf_d, nf_e, lateral;
+    /* structured light cleanPointCloud pass-through limits (SL.cpp:39-40,51-66) */
+    double cutoff_min, cutoff_max;
 } orc_sensor;
+
+/* SensorProcessorBase::process -> cleanPointCloud (SPB.cpp:90), run before Process_points.
+ * laser: pcl::removeNaNFromPointCloud (Laser.cpp:50-59) drops points with a non-finite x, y or z;
+ * structured light: pcl::PassThrough on field "z" with limits (float)cutoff_min/max (SL.cpp:51-66)
+ * drops non-finite points and points with z < min || z > max.
+ * PCL is an un-vendored, unpinned dependency of the reference: both filters are restated from
+ * PCL's published algorithm (filters/impl/passthrough.hpp, filters/impl/filter.hpp) -> this
+ * function is PARITY UNPINNED.  Compacts xyzi (n x 4 floats) and rgba (n x 4 bytes, may be NULL)
+ * in place, order preserved; returns the number of points kept. */
+int orc_clean_point_cloud(const orc_sensor *sensor, int n, float *xyzi, unsigned char *rgba);
 
 /* gpu.cu:940-994 + G_Init_map :198-214 */
 orc_map *orc_create(int length, float resolution, float mahalanobis, float obstacle_threshold);

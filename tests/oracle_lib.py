@@ -27,7 +27,7 @@ class OrcMap(C.Structure):
 class OrcSensor(C.Structure):
     _fields_ = [("type", C.c_int), ("min_r", C.c_float), ("beam_a", C.c_float), ("beam_c", C.c_float),
                 ("nf_a", C.c_double), ("nf_b", C.c_double), ("nf_c", C.c_double), ("nf_d", C.c_double),
-                ("nf_e", C.c_double), ("lateral", C.c_double)]
+                ("nf_e", C.c_double), ("lateral", C.c_double), ("cutoff_min", C.c_double), ("cutoff_max", C.c_double)]
 
 
 _lib = None
@@ -72,6 +72,8 @@ def load():
     lib.orc_show.argtypes = [MP, C.c_double, P, P, P, P, P, P, P, P, C.POINTER(C.c_int)]
     lib.orc_harvest.argtypes = [C.c_int, C.c_double, P, P, P, P, P, P, P, P, P, P, P, P, C.POINTER(C.c_int)]
     lib.orc_colourise.argtypes = [P, C.c_int, P, P, P, C.c_int, C.c_int, C.c_int, P]
+    lib.orc_clean_point_cloud.restype = C.c_int
+    lib.orc_clean_point_cloud.argtypes = [C.POINTER(OrcSensor), C.c_int, P, P]
     lib.orc_add_points_mt.argtypes = [MP, C.c_int, P, P, P, C.c_double, C.c_double, C.POINTER(OrcSensor), P, C.c_int]
     _lib = lib
     return lib
@@ -96,7 +98,8 @@ def colourise(xyzi, T_camera, T_lidar, bgr):
 def sensor_from_frame(frame) -> OrcSensor:
     s = frame.sensor
     return OrcSensor(s.type, s.min_radius, s.beam_angle, s.beam_constant, s.normal_factor_a, s.normal_factor_b,
-                     s.normal_factor_c, s.normal_factor_d, s.normal_factor_e, s.lateral_factor)
+                     s.normal_factor_c, s.normal_factor_d, s.normal_factor_e, s.lateral_factor,
+                     s.cutoff_min_depth, s.cutoff_max_depth)
 
 
 class OracleMap:
@@ -167,6 +170,7 @@ class OracleMap:
         if n is not None:
             xyzi = xyzi[:n]
             rgba = None if rgba is None else rgba[:n]
+        xyzi, rgba = self.clean_point_cloud(xyzi, rgba, frame)
         key, var, xt, yt, zt = self.process_points(xyzi[:, 0], xyzi[:, 1], xyzi[:, 2], frame)
         if rgba is None:
             R = G = B = np.zeros(xyzi.shape[0], np.int32)
@@ -174,7 +178,17 @@ class OracleMap:
             R, G, B = (rgba[:, k].astype(np.int32) for k in range(3))
         self.fuse_points(key, R, G, B, xyzi[:, 3], zt, var)
 
+    def clean_point_cloud(self, xyzi, rgba, frame):
+        """SensorProcessorBase::process's cleanPointCloud (SPB.cpp:90): copies, like the reference (:83-87), and
+        removes the points the sensor processor drops before Process_points"""
+        xyzi = np.array(xyzi, np.float32, copy=True, order="C")
+        rgba = None if rgba is None else np.array(rgba, np.uint8, copy=True, order="C")
+        sensor = sensor_from_frame(frame)
+        k = self.lib.orc_clean_point_cloud(C.byref(sensor), xyzi.shape[0], _p(xyzi), _p(rgba))
+        return xyzi[:k], (None if rgba is None else rgba[:k])
+
     def add_mt(self, xyzi, rgba, frame, nthreads):
+        xyzi, rgba = self.clean_point_cloud(xyzi, rgba, frame)
         xyzi = np.ascontiguousarray(xyzi, np.float32)
         rgba = None if rgba is None else np.ascontiguousarray(rgba, np.uint8)
         T = np.array(frame.T[:], np.float32)

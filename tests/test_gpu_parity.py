@@ -198,7 +198,13 @@ def test_multi_frame_stream_with_scroll_and_cleanup():
 
 
 def test_structured_light_c3_small():
+    """config c3: the raw 640x480 D435 image (NaN where there is no return, depths beyond the useful range kept)
+    through the fused add; cleanPointCloud's depth pass-through (StructuredLightSensorProcessor.cpp:51-66) is part
+    of the path: the oracle really removes the points (orc_clean_point_cloud), the device rejects them in place"""
     fr = synth.d435_frame(0)
+    z = fr["xyzi"][:, 2]
+    assert fr["xyzi"].shape[0] == 640 * 480
+    assert np.isnan(z).sum() > 100 and (z > 3.25).sum() > 1000 and ((z >= 0.2) & (z <= 3.25)).sum() > 50000
     sp = gem_b200.StructuredLightSensorProcessor()
     f = gem_b200.make_frame(fr["T"], sp, base_z=0.0)
     g, o = both(512, 0.02, compat_box_filter=False)
@@ -207,6 +213,25 @@ def test_structured_light_c3_small():
         m.add(fr["xyzi"], fr["rgba"], f)
     assert_layers_equal(g, o, what="structured light")
     assert (o.get_layer("elevation") != -10).sum() > 5000
+    assert g.stats()["points_binned"] <= int(((z >= 0.2) & (z <= 3.25)).sum())
+    # the filter bites: with the pass-through wide open more points reach the map
+    wide = gem_b200.StructuredLightSensorProcessor(cutoff_min_depth=-1e30, cutoff_max_depth=1e30)
+    fw = gem_b200.make_frame(fr["T"], wide, base_z=0.0)
+    g2, o2 = both(512, 0.02, compat_box_filter=False)
+    for m in (g2, o2):
+        m.move(fr["position"])
+        m.add(fr["xyzi"], fr["rgba"], fw)
+    assert_layers_equal(g2, o2, what="structured light, pass-through wide open")
+    assert g2.stats()["points_binned"] > g.stats()["points_binned"]
+    # limits are compared as floats and inclusive (pcl::PassThrough): a point exactly on a limit is kept
+    edge = np.array([[0.0, 0.0, np.float32(0.2), 9.0], [0.0, 0.0, np.nextafter(np.float32(0.2), np.float32(0)), 9.0],
+                     [0.0, 0.0, np.float32(3.25), 9.0], [0.0, 0.0, np.nextafter(np.float32(3.25), np.float32(9)), 9.0]], np.float32)
+    g3, o3 = both(64, 0.1, compat_box_filter=False)
+    fe = gem_b200.make_frame(np.eye(4), sp, base_z=0.0)
+    for m in (g3, o3):
+        m.add(edge, None, fe)
+    assert_layers_equal(g3, o3, what="pass-through limits")
+    assert g3.stats()["points_binned"] == 2
 
 
 def test_rotation_variance_term():

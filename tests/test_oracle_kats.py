@@ -337,3 +337,30 @@ def test_colourise_kats():
     assert np.array_equal(c2[:, 3] == 255, ok) and 500 < ok.sum() < 4500
     assert np.array_equal(c2[ok, 2], bgr[my[ok], mx[ok], 0]) and np.array_equal(c2[ok, 1], bgr[my[ok], mx[ok], 1])
     assert (x2[~ok, 3] == 0).all() and (x2[ok, 3] == 7).all()
+
+
+def test_clean_point_cloud_kats():
+    """SensorProcessorBase::process -> cleanPointCloud (SPB.cpp:90): laser removes non-finite points
+    (Laser.cpp:50-59), structured light additionally applies the inclusive float pass-through on z (SL.cpp:51-66);
+    order of the survivors is kept and the caller's cloud is not modified (the reference works on a copy, SPB.cpp:83-87)"""
+    import gem_b200
+    from oracle_lib import OracleMap
+    o = OracleMap(16, 0.1, compat_box_filter=False)
+    nan, inf = np.float32(np.nan), np.float32(np.inf)
+    pts = np.array([[0, 0, 0.1, 1], [0, 0, 0.2, 2], [nan, 0, 1.0, 3], [0, inf, 1.0, 4], [0, 0, 3.25, 5],
+                    [0, 0, 3.2500002, 6], [0, 0, nan, 7], [1, 1, 1.0, 8], [0, 0, -0.5, 9]], np.float32)
+    rgba = (np.arange(36, dtype=np.uint8).reshape(9, 4) + 1)
+    keep_before = pts.copy()
+    sl = gem_b200.make_frame(np.eye(4), gem_b200.StructuredLightSensorProcessor())
+    x, c = o.clean_point_cloud(pts, rgba, sl)
+    assert x[:, 3].tolist() == [2, 5, 8] and c[:, 0].tolist() == [5, 17, 29]
+    la = gem_b200.make_frame(np.eye(4), gem_b200.LaserSensorProcessor())
+    x, c = o.clean_point_cloud(pts, rgba, la)
+    assert x[:, 3].tolist() == [1, 2, 5, 6, 8, 9]
+    assert np.array_equal(pts, keep_before, equal_nan=True)
+    # the node's defaults (DBL_MIN, DBL_MAX -> float 0, +inf): negative depths go, everything finite else stays
+    import sys
+    dflt = gem_b200.make_frame(np.eye(4), gem_b200.StructuredLightSensorProcessor(
+        cutoff_min_depth=sys.float_info.min, cutoff_max_depth=sys.float_info.max))
+    x, _ = o.clean_point_cloud(pts, None, dflt)
+    assert x[:, 3].tolist() == [1, 2, 5, 6, 8]
