@@ -57,7 +57,7 @@ class GemProfile(C.Structure):
     _fields_ = [("launches", C.c_longlong), ("ms", C.c_double * 9), ("count", C.c_longlong * 9)]
 
 
-PROF_CLASSES = ["transform_bin", "alloc_cells", "scatter", "fold", "clear_floor", "features", "raytrace", "other", "add_fused"]
+PROF_CLASSES = ["transform_bin", "alloc_cells", "scatter", "fold", "clear_floor", "features", "raytrace", "other", "route"]
 
 # every symbol include/gem_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -70,7 +70,7 @@ SYMBOLS = {
     "gem_destroy": (C.c_int, [_P]),
     "gem_sync": (C.c_int, [_P]),
     "gem_get_stream": (C.c_void_p, [_P]),
-    "gem_debug_phase_stamps": (C.c_int, [_P, C.c_int, C.POINTER(C.c_ulonglong)]),
+    "gem_flush": (C.c_int, [_P]),
     "gem_move": (C.c_int, [_P, _FP, _FP, _IP, _FP]),
     "gem_add_points": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),
     "gem_add_points_host": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),

@@ -16,7 +16,6 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgem_b200.so")
-FACADE_LIB = os.path.join(LIBDIR, "libgem_b200_cxx.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -49,7 +48,7 @@ def sources() -> list[str]:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile libgem_b200.so (kernels + C ABI) and the C++ facade library."""
+    """Compile libgem_b200.so (kernels + C ABI; the C++ facade is header-only)."""
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = sources()
     if force or not _newer(LIB, srcs):
@@ -57,11 +56,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
-        subprocess.run(cmd, check=True, cwd=CSRC)
-    facade_src = os.path.join(CSRC, "elevation_map.cpp")
-    if os.path.exists(facade_src) and (force or not _newer(FACADE_LIB, srcs + [LIB])):
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
-               "-o", FACADE_LIB, facade_src, "-L", LIBDIR, "-lgem_b200", "-Wl,-rpath,$ORIGIN"]
         subprocess.run(cmd, check=True, cwd=CSRC)
     return LIB
 

@@ -5,7 +5,9 @@
 // Map_closeloop :1235, Map_feature :1256, Raytracing :1304).  Differences by design:
 // per-handle state instead of __device__ globals, one stream per handle, zero per-call
 // cudaMalloc/cudaFree (the reference does 8+7+9 per frame), geometry passed as kernel
-// parameters instead of cudaMemcpyTo/FromSymbol round trips, int status codes.
+// parameters instead of cudaMemcpyTo/FromSymbol round trips, int status codes, and every entry
+// point takes the handle's mutex (the reference node enters libgpu.so from three threads,
+// ElevationMapping.cpp:271-300,388-421, only partly under MapMutex_).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -14,10 +16,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/gem_b200.h"
+#include "gem_add.cuh"
 #include "gem_kernels.cuh"
 #include "gem_route.cuh"
 
@@ -29,7 +34,23 @@ thread_local std::string g_create_error;
 
 } // namespace
 
+// one add call whose bin kernel has been issued and whose fold has not (pipelined mode)
+struct PendingFold {
+    bool active = false;
+    BinScratch sc{};
+    FoldSrc src{};
+    MapGeom geom{};   // the geometry the call was binned with (a later Move must not change its lowest indices)
+    int n = 0;
+};
+
+struct FrameGraph { // {fold of the previous call || bin of this call} as one two-node CUDA graph
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t fold_node = nullptr, bin_node = nullptr;
+};
+
 struct gem_map {
+    std::recursive_mutex mu;
     gem_config cfg{};
     int dev = 0;
     cudaStream_t stream = nullptr;
@@ -39,50 +60,46 @@ struct gem_map {
     int P = 0;     // per-launch point capacity
     MapGeom geom{};
     MapLayers ml{};
-    Scratch sc{};
     float sensorZ = 0.0f;
+    // add path: two scratch sets (call parity), three counter buffers (the bin kernel of call i zeroes the
+    // buffer of call i+1, last used by call i-2 whose fold is complete by then)
+    BinScratch bs[2]{};
+    BinCounters *ctr[3] = {nullptr, nullptr, nullptr};
+    unsigned call_no = 0;
+    BinCounters *ctr_last = nullptr; // counters of the last add call
+    PendingFold pend;
+    int pipe_mode = 2;               // 0: never defer the fold; 1: two streams + events; 2: CUDA graph per call
+    std::map<const void *, FrameGraph> graphs; // keyed by the bin kernel function
+    cudaStream_t front_stream = nullptr;      // pipe_mode 1: the bin kernels run here
+    cudaEvent_t ev_bin[2] = {nullptr, nullptr}, ev_fold[2] = {nullptr, nullptr}, ev_mark = nullptr;
     // deferred region operations (scroll clears of Move, the every-cell variance floor of
     // G_fuse): executed by the next add/fuse launch, or flushed before anything observes the map
     std::vector<RegionOp> pending;
-    Counters *ctr_buf[2] = {nullptr, nullptr};
-    int ctr_cur = 0;          // which counter buffer the NEXT call uses (it is zero)
-    Counters *ctr_last = nullptr; // counters of the last finished call
-    bool pdl = false;         // programmatic dependent launch between the add-path kernels (opt-in)
-    bool pdl_front = false;   // stream mode only: PDL between transform -> alloc -> scatter on the front stream (opt-in)
-    int coop_blocks = 0;      // co-resident grid size of the fused kernel (0 = unavailable)
-    int fused_max_points = 1 << 20;
     // staging (device), lazily allocated
     void *d_xyzi = nullptr, *d_rgba = nullptr, *d_pcl = nullptr;
     float *d_x = nullptr, *d_y = nullptr, *d_z = nullptr, *d_xt = nullptr, *d_yt = nullptr;
-    int *d_keyin = nullptr, *d_R = nullptr, *d_G = nullptr, *d_B = nullptr;
-    float *d_int = nullptr;
+    int *d_keyin = nullptr, *d_keyout = nullptr, *d_R = nullptr, *d_G = nullptr, *d_B = nullptr;
+    float *d_int = nullptr, *d_h = nullptr, *d_hv = nullptr;
     float *d_out = nullptr; // 9 * nc floats read-out staging
     int *d_owner_cnt = nullptr;
+    RouteScratch route_sc{};
     float2 *prev_ev = nullptr;     // gem_snapshot_shown: prevMap_ (ElevationMapping.cpp:422) on the device
     uint2 *prev_ci = nullptr;
     float *prev_tr = nullptr;
     MapGeom prev_geom{};
     bool prev_valid = false;
     int *d_viscnt = nullptr;       // visual-cloud export: per (column, row chunk) counts / offsets
-    uint32_t *d_gbitmap = nullptr; // tiled ray clean-up: validity bitmap of the map-wide lowest layer
-    Counters *h_ctr = nullptr; // pinned
-    // pipelined host ingest (gem_add_points_host_async)
+    int *d_raylist = nullptr;      // ray clean-up: cells that cast a ray + their count
+    uint32_t *d_bitmap = nullptr;  // ray clean-up: validity bitmap of the lowest layer (own tile / map-wide)
+    size_t bitmap_words = 0;
+    BinCounters *h_ctr = nullptr; // pinned
+    // pipelined host ingest (gem_add_points_host_async): three staging sets (the fold of call i, issued with
+    // call i+1, still reads call i's intensities)
     cudaStream_t copy_stream = nullptr;
-    void *d_axyzi[2] = {nullptr, nullptr}, *d_argba[2] = {nullptr, nullptr};
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    Counters *h_ctr_ring = nullptr; // pinned, 2 entries
+    void *d_axyzi[3] = {nullptr, nullptr, nullptr}, *d_argba[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_h2d[3] = {nullptr, nullptr, nullptr}, ev_done[3] = {nullptr, nullptr, nullptr};
+    BinCounters *h_ctr_ring = nullptr; // pinned, 2 entries
     unsigned async_calls = 0;
-    // gem_add_points_stream: frame-pipelined mode (own scratch sets, front stream, events)
-    bool pipe_ready = false;
-    // frame pipeline of gem_add_points_stream: three stages on three streams (transform+bin | alloc+scatter | fold),
-    // three scratch sets (one per frame in flight), four counter buffers (the transform kernel of frame i clears
-    // the buffer of frame i+1, last used by frame i-3)
-    Scratch pipe_sc[3];
-    Counters *pipe_ctr[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t front_stream = nullptr, mid_stream = nullptr;
-    bool mid_owned = false;
-    cudaEvent_t ev_bin[3] = {nullptr, nullptr, nullptr}, ev_front[3] = {nullptr, nullptr, nullptr}, ev_fold[3] = {nullptr, nullptr, nullptr};
-    unsigned pipe_calls = 0;
     // gem_add_points_multi: ring of per-call FrameParams tables (pinned host + device)
     FrameParams *h_frames = nullptr, *d_frames = nullptr;
     cudaEvent_t ev_frames[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -102,6 +119,8 @@ struct gem_map {
 
 namespace {
 
+using Lock = std::lock_guard<std::recursive_mutex>;
+
 int fail(gem_map *m, int code, const std::string &msg)
 {
     if (m) m->err = msg; else g_create_error = msg;
@@ -120,7 +139,7 @@ cudaEvent_t prof_event(gem_map *m)
     return e;
 }
 // every kernel launch of the library goes through this macro: counts the launch and, when
-// profiling is on, brackets it with CUDA events on the handle's stream
+// profiling is on, brackets it with CUDA events on the stream it is launched on
 #define GEM_LAUNCH_ON(m, st, cls, ...)                           \
     do {                                                         \
         (m)->launches++;                                         \
@@ -134,36 +153,7 @@ cudaEvent_t prof_event(gem_map *m)
             __VA_ARGS__;                                         \
         }                                                        \
     } while (0)
-#define GEM_LAUNCH(m, cls, ...)                                  \
-    do {                                                         \
-        (m)->launches++;                                         \
-        if ((m)->profiling) {                                    \
-            gem_map::Span sp__{(cls), prof_event(m), prof_event(m)}; \
-            cudaEventRecord(sp__.e0, (m)->stream);               \
-            __VA_ARGS__;                                         \
-            cudaEventRecord(sp__.e1, (m)->stream);               \
-            (m)->spans.push_back(sp__);                          \
-        } else {                                                 \
-            __VA_ARGS__;                                         \
-        }                                                        \
-    } while (0)
-
-// launch with programmatic stream serialization (PDL); falls back to a plain launch when disabled
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args)
-{
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)block);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
+#define GEM_LAUNCH(m, cls, ...) GEM_LAUNCH_ON(m, (m)->stream, cls, __VA_ARGS__)
 
 #define GEM_CUDA(m, expr)                                                                      \
     do {                                                                                       \
@@ -250,10 +240,33 @@ int launch_regions(gem_map *m, const RegionOp *ops, int count)
     return GEM_OK;
 }
 
-// something is about to read the layers: execute deferred clears now (a clear is visible in
-// the reference as soon as Move returns); floors stay pending until the next Fuse
+// ---- the fold of a pipelined add call is issued with the NEXT call, or here ------------------------------------
+int launch_fold(gem_map *m, cudaStream_t st, const PendingFold &p, const RegionOps &ro, int region_blocks, bool do_fuse, bool do_lowest)
+{
+    const int fb = blocks_for((size_t)p.n, ADD_BLOCK, 148 * 8);
+    GEM_LAUNCH_ON(m, st, GEM_PROF_FOLD, k_fold<<<fb + region_blocks, ADD_BLOCK, 0, st>>>(p.geom, m->ml, p.sc, p.src, ro, fb, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
+int drain(gem_map *m)
+{
+    if (!m->pend.active) return GEM_OK;
+    if (m->pipe_mode == 1) GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_bin[m->pend.sc.par], 0));
+    RegionOps none{};
+    int rc = launch_fold(m, m->stream, m->pend, none, 0, true, true);
+    if (rc) return rc;
+    if (m->pipe_mode == 1) GEM_CUDA(m, cudaEventRecord(m->ev_fold[m->pend.sc.par], m->stream));
+    m->pend.active = false;
+    return GEM_OK;
+}
+
+// something is about to read the layers: issue a deferred fold, then execute deferred clears (a clear is visible
+// in the reference as soon as Move returns); floors stay pending until the next Fuse
 int flush_for_observer(gem_map *m)
 {
+    int rc = drain(m);
+    if (rc) return rc;
     std::vector<RegionOp> now;
     for (RegionOp &r : m->pending)
         if (r.clear) {
@@ -266,8 +279,8 @@ int flush_for_observer(gem_map *m)
     return launch_regions(m, now.data(), (int)now.size());
 }
 
-// a Fuse-type call is starting: hand the pending operations to its first kernel.  Returns the
-// number of extra blocks that kernel should carry.
+// a Fuse-type call is starting with nothing in flight: hand the pending operations to its first kernel.
+// The operations leave the pending list only once the kernel that executes them has been launched (commit_region_ops).
 int take_region_ops(gem_map *m, RegionOps &ro, int &region_blocks)
 {
     ro.count = 0;
@@ -283,17 +296,19 @@ int take_region_ops(gem_map *m, RegionOps &ro, int &region_blocks)
         ro.op[ro.count++] = r;
         cells += region_cells(m, r);
     }
-    m->pending.clear();
     if (ro.count) region_blocks = blocks_for(cells, ADD_BLOCK * 4, 148 * 2);
     return GEM_OK;
 }
+void commit_region_ops(gem_map *m) { m->pending.clear(); }
 
 // a Fuse with nothing to fold still applies clears + floor
 int flush_all_pending(gem_map *m)
 {
+    int rc = drain(m);
+    if (rc) return rc;
     if (m->pending.empty()) return GEM_OK;
-    int rc = launch_regions(m, m->pending.data(), (int)m->pending.size());
-    m->pending.clear();
+    rc = launch_regions(m, m->pending.data(), (int)m->pending.size());
+    if (rc == GEM_OK) m->pending.clear();
     return rc;
 }
 
@@ -303,60 +318,44 @@ void pend_all_floor(gem_map *m)
     m->pending.push_back(RegionOp{0, 0, 0, 0, 1});
 }
 
-Scratch cur_scratch(gem_map *m)
-{
-    Scratch sc = m->sc;
-    sc.ctr = m->ctr_buf[m->ctr_cur];
-    sc.ctr_next = m->ctr_buf[m->ctr_cur ^ 1];
-    return sc;
-}
-void call_done(gem_map *m)
-{
-    m->ctr_last = m->ctr_buf[m->ctr_cur];
-    m->ctr_cur ^= 1;
-}
-
-// points per thread in the transform / scatter kernels: one point per thread keeps a frame-sized call
-// (1e5 points, < 1 wave) latency-optimal; large calls get 2 or 4 points per thread so that a thread has
-// several independent DRAM/L2 round trips in flight instead of running 3-4 waves of serial chains
+// points per thread in the bin kernel: one point per thread keeps a frame-sized call (1e5 points, < 1 wave)
+// latency-optimal; large calls get 2 or 4 points per thread so that a thread has several independent DRAM/L2
+// round trips in flight instead of running 3-4 waves of serial chains
 inline int points_per_thread(int n) { return n >= 600000 ? 4 : (n >= 250000 ? 2 : 1); }
 
-// K2..K4 after the binning kernel of the current chunk
-template <int ATTR>
-int run_group_fold(gem_map *m, const Scratch &sc, const AttrInput &a, int n, bool do_fuse, bool do_lowest)
+typedef void (*BinKernel)(MapGeom, MapLayers, FrameParams, BinSource, int, BinScratch, RegionOps, int, const SegTable, const FrameParams *);
+template <int SRC> BinKernel bin_kernel(int U)
 {
-    GEM_LAUNCH(m, GEM_PROF_ALLOC, launch_pdl(m->pdl, k_alloc_cells, blocks_for((size_t)n, ADD_BLOCK, 148 * 4), ADD_BLOCK, m->stream, sc));
-    const int U = points_per_thread(n);
-    const int sb = blocks_for((size_t)(n + U - 1) / U, ADD_BLOCK, 148 * 16);
-    if (U == 4) GEM_LAUNCH(m, GEM_PROF_SCATTER, launch_pdl(m->pdl, k_scatter<ATTR, 4>, sb, ADD_BLOCK, m->stream, a, n, sc));
-    else if (U == 2) GEM_LAUNCH(m, GEM_PROF_SCATTER, launch_pdl(m->pdl, k_scatter<ATTR, 2>, sb, ADD_BLOCK, m->stream, a, n, sc));
-    else GEM_LAUNCH(m, GEM_PROF_SCATTER, launch_pdl(m->pdl, k_scatter<ATTR, 1>, sb, ADD_BLOCK, m->stream, a, n, sc));
-    GEM_LAUNCH(m, GEM_PROF_FOLD, launch_pdl(m->pdl, k_fold, blocks_for((size_t)n, ADD_BLOCK, 148 * 8), ADD_BLOCK, m->stream, m->geom, m->ml, sc, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
-    GEM_CUDA(m, cudaGetLastError());
-    call_done(m);
-    return GEM_OK;
+    if (SRC == SRC_XYZI || SRC == SRC_RECORDS) {
+        if (U == 4) return k_bin<SRC, 4>;
+        if (U == 2) return k_bin<SRC, 2>;
+    }
+    return k_bin<SRC, 1>;
 }
 
 int read_counters(gem_map *m, long long n_in, bool accumulate)
 {
-    GEM_CUDA(m, cudaMemcpyAsync(m->h_ctr, m->ctr_last, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+    int rc = drain(m);
+    if (rc) return rc;
+    GEM_CUDA(m, cudaMemcpyAsync(m->h_ctr, m->ctr_last, sizeof(BinCounters), cudaMemcpyDeviceToHost, m->stream));
     GEM_CUDA(m, cudaStreamSynchronize(m->stream));
     if (!accumulate) memset(&m->stats, 0, sizeof m->stats);
     m->stats.points_in += n_in;
     m->stats.points_binned += m->h_ctr->total;
     m->stats.cells_touched += m->h_ctr->ntouched;
-    int mk = m->h_ctr->maxk; // only lists longer than FOLD_SMALL_K are tracked exactly
-    if (mk < 1 && m->h_ctr->ntouched > 0) mk = (m->h_ctr->total > m->h_ctr->ntouched) ? FOLD_SMALL_K : 1;
+    if (m->h_ctr->pool > m->bs[0].pool_cap) return fail(m, GEM_ERR_CUDA, "internal: record pool exhausted");
+    int mk = m->h_ctr->maxk; // only lists longer than 8 are tracked exactly
+    if (mk < 1 && m->h_ctr->ntouched > 0) mk = (m->h_ctr->total > m->h_ctr->ntouched) ? CHUNK0 : 1;
     if (mk > m->stats.max_points_per_cell) m->stats.max_points_per_cell = mk;
     return GEM_OK;
 }
 
 int ensure_host_staging(gem_map *m)
 {
-    if (m->d_xyzi) return GEM_OK;
+    if (m->d_xyzi && m->d_rgba) return GEM_OK;
     int rc;
-    if ((rc = dev_alloc(m, (float4 **)&m->d_xyzi, (size_t)m->P))) return rc;
-    if ((rc = dev_alloc(m, (uchar4 **)&m->d_rgba, (size_t)m->P))) return rc;
+    if (!m->d_xyzi && (rc = dev_alloc(m, (float4 **)&m->d_xyzi, (size_t)m->P))) return rc;
+    if (!m->d_rgba && (rc = dev_alloc(m, (uchar4 **)&m->d_rgba, (size_t)m->P))) return rc;
     return GEM_OK;
 }
 int ensure_pcl_staging(gem_map *m)
@@ -366,19 +365,12 @@ int ensure_pcl_staging(gem_map *m)
 }
 int ensure_compat_staging(gem_map *m)
 {
-    if (m->d_x) return GEM_OK;
     int rc;
     const size_t P = (size_t)m->P;
-    if ((rc = dev_alloc(m, &m->d_x, P))) return rc;
-    if ((rc = dev_alloc(m, &m->d_y, P))) return rc;
-    if ((rc = dev_alloc(m, &m->d_z, P))) return rc;
-    if ((rc = dev_alloc(m, &m->d_xt, P))) return rc;
-    if ((rc = dev_alloc(m, &m->d_yt, P))) return rc;
-    if ((rc = dev_alloc(m, &m->d_keyin, P))) return rc;
-    if ((rc = dev_alloc(m, &m->d_R, P))) return rc;
-    if ((rc = dev_alloc(m, &m->d_G, P))) return rc;
-    if ((rc = dev_alloc(m, &m->d_B, P))) return rc;
-    if ((rc = dev_alloc(m, &m->d_int, P))) return rc;
+    float **fp[] = {&m->d_x, &m->d_y, &m->d_z, &m->d_xt, &m->d_yt, &m->d_int, &m->d_h, &m->d_hv};
+    int **ip[] = {&m->d_keyin, &m->d_keyout, &m->d_R, &m->d_G, &m->d_B};
+    for (float **p : fp) if (!*p && (rc = dev_alloc(m, p, P))) return rc; // each buffer once, also after a partial failure
+    for (int **p : ip) if (!*p && (rc = dev_alloc(m, p, P))) return rc;
     return GEM_OK;
 }
 int ensure_out_staging(gem_map *m)
@@ -387,42 +379,151 @@ int ensure_out_staging(gem_map *m)
     return dev_alloc(m, &m->d_out, m->nc * 9);
 }
 
-// one chunk of the fused path on device-resident input
-template <int IN, int ATTR>
-int add_chunk(gem_map *m, const PointInput &in, const AttrInput &a, int n, const FrameParams &fp)
+int ensure_ray_scratch(gem_map *m, size_t bitmap_cells)
 {
-    RegionOps ro;
-    int rb = 0;
-    int rc = take_region_ops(m, ro, rb);
-    if (rc) return rc;
-    const Scratch sc = cur_scratch(m);
-    if (m->coop_blocks > 0 && n <= m->fused_max_points) {
-        // frame-sized call: one cooperative launch, grid barriers between the phases
-        MapGeom g = m->geom;
-        MapLayers ml = m->ml;
-        FrameParams f = fp;
-        PointInput pin = in;
-        AttrInput at = a;
-        int nn = n, do_fuse = 1, do_lowest = 1;
-        Scratch s2 = sc;
-        void *args[] = {&g, &ml, &f, &pin, &at, &nn, &s2, &ro, &do_fuse, &do_lowest};
-        int blocks = blocks_for((size_t)(n > 0 ? n : 1), ADD_BLOCK, m->coop_blocks);
-        if (ro.count && blocks < m->coop_blocks) blocks = (blocks + rb < m->coop_blocks) ? blocks + rb : m->coop_blocks;
-        GEM_LAUNCH(m, GEM_PROF_FUSED,
-                   cudaLaunchCooperativeKernel((const void *)k_add_fused<IN, ATTR>, dim3(blocks), dim3(ADD_BLOCK), args, 0, m->stream));
-        GEM_CUDA(m, cudaGetLastError());
-        call_done(m);
-        return GEM_OK;
+    int rc;
+    if (!m->d_raylist && (rc = dev_alloc(m, &m->d_raylist, m->nc + 1))) return rc; // every cell may cast a ray; [nc] = the count
+    const size_t words = bitmap_cells / 32 + 1;
+    if (!m->d_bitmap || m->bitmap_words < words) {
+        if ((rc = dev_alloc(m, &m->d_bitmap, words))) return rc;
+        m->bitmap_words = words;
     }
+    return GEM_OK;
+}
+int ensure_route_scratch(gem_map *m)
+{
+    int rc;
+    const size_t P = (size_t)m->P;
+    RouteScratch &r = m->route_sc;
+    if (!r.owner && (rc = dev_alloc(m, &r.owner, P))) return rc;
+    if (!r.gkey && (rc = dev_alloc(m, &r.gkey, P))) return rc;
+    if (!r.h && (rc = dev_alloc(m, &r.h, P))) return rc;
+    if (!r.hv && (rc = dev_alloc(m, &r.hv, P))) return rc;
+    if (!r.blockCounts) {
+        r.blockCounts_capacity = (size_t)ROUTE_MAX_OWNERS * ((P + ROUTE_BLOCK - 1) / ROUTE_BLOCK);
+        if ((rc = dev_alloc(m, &r.blockCounts, r.blockCounts_capacity))) return rc;
+    }
+    return GEM_OK;
+}
+
+int pipe_setup(gem_map *m)
+{
+    if (m->pipe_mode != 1) return GEM_OK;
+    if (!m->front_stream) GEM_CUDA(m, cudaStreamCreateWithFlags(&m->front_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        if (!m->ev_bin[i]) GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_bin[i], cudaEventDisableTiming));
+        if (!m->ev_fold[i]) {
+            GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_fold[i], cudaEventDisableTiming));
+            GEM_CUDA(m, cudaEventRecord(m->ev_fold[i], m->stream));
+        }
+    }
+    if (!m->ev_mark) GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_mark, cudaEventDisableTiming));
+    return GEM_OK;
+}
+
+// {fold(previous call) || bin(this call)} as a two-node graph, built once per bin kernel; per call only the node
+// parameters change.  One cudaGraphLaunch replaces two launches, two event records and two stream waits.
+int launch_frame_graph(gem_map *m, BinKernel bk, void **bin_args, int bin_grid, void **fold_args, int fold_grid)
+{
+    FrameGraph &fg = m->graphs[(const void *)bk];
+    cudaKernelNodeParams kb{}, kf{};
+    kb.func = (void *)bk; kb.gridDim = dim3((unsigned)bin_grid); kb.blockDim = dim3(ADD_BLOCK); kb.sharedMemBytes = 0; kb.kernelParams = bin_args;
+    kf.func = (void *)k_fold; kf.gridDim = dim3((unsigned)fold_grid); kf.blockDim = dim3(ADD_BLOCK); kf.sharedMemBytes = 0; kf.kernelParams = fold_args;
+    if (!fg.exec) {
+        GEM_CUDA(m, cudaGraphCreate(&fg.graph, 0));
+        GEM_CUDA(m, cudaGraphAddKernelNode(&fg.fold_node, fg.graph, nullptr, 0, &kf));
+        GEM_CUDA(m, cudaGraphAddKernelNode(&fg.bin_node, fg.graph, nullptr, 0, &kb));
+        GEM_CUDA(m, cudaGraphInstantiate(&fg.exec, fg.graph, 0));
+    } else {
+        GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(fg.exec, fg.fold_node, &kf));
+        GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(fg.exec, fg.bin_node, &kb));
+    }
+    GEM_CUDA(m, cudaGraphLaunch(fg.exec, m->stream));
+    m->launches += 2;
+    return GEM_OK;
+}
+
+// One add call on device-resident input.  pipelined == false: bin (+ deferred region operations) then fold, both
+// on the handle's stream.  pipelined == true: the bin kernel of this call is issued together with the FOLD OF THE
+// PREVIOUS pipelined call (which also carries the row / column clears this call's Move decided), and this call's
+// fold stays pending until the next call or until anything observes the map (drain).
+template <int SRC>
+int enqueue_add(gem_map *m, const BinSource &in, const FoldSrc &fsrc, int n, const FrameParams &fp, const SegTable *segs,
+                const FrameParams *frames, bool pipelined, bool do_fuse, bool do_lowest)
+{
+    int rc;
+    if (m->profiling || m->pipe_mode == 0) pipelined = false; // per-kernel event timing needs the serial schedule
+    if (pipelined && (rc = pipe_setup(m))) return rc;
+    if (pipelined && m->pend.active) {
+        // operations other than "clear + floor of a row / column band" cannot ride on a running fold
+        bool mergeable = (int)m->pending.size() <= MAX_REGION_OPS;
+        for (const RegionOp &r : m->pending) mergeable = mergeable && r.kind != 0 && r.clear && r.floor_;
+        if (!mergeable && (rc = drain(m))) return rc;
+    }
+    if (!pipelined && (rc = drain(m))) return rc;
+    const int par = (int)(m->call_no & 1u), c = (int)(m->call_no % 3u);
+    BinScratch sc = m->bs[par];
+    sc.ctr = m->ctr[c];
+    sc.ctr_next = m->ctr[(c + 1) % 3];
+    sc.par = par;
     const int U = points_per_thread(n);
+    BinKernel bk = bin_kernel<SRC>(U);
     const int pb = blocks_for((size_t)(n + U - 1) / U, ADD_BLOCK, 148 * 16);
-    if (U == 4)
-        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, launch_pdl(m->pdl, k_transform_bin<IN, 4>, pb + rb, ADD_BLOCK, m->stream, m->geom, m->ml, fp, in, n, sc, ro, pb, (float *)nullptr, (float *)nullptr));
-    else if (U == 2)
-        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, launch_pdl(m->pdl, k_transform_bin<IN, 2>, pb + rb, ADD_BLOCK, m->stream, m->geom, m->ml, fp, in, n, sc, ro, pb, (float *)nullptr, (float *)nullptr));
-    else
-        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, launch_pdl(m->pdl, k_transform_bin<IN, 1>, pb + rb, ADD_BLOCK, m->stream, m->geom, m->ml, fp, in, n, sc, ro, pb, (float *)nullptr, (float *)nullptr));
-    return run_group_fold<ATTR>(m, sc, a, n, true, true);
+    SegTable st{};
+    if (segs) st = *segs;
+    MapGeom g = m->geom;
+    MapLayers ml = m->ml;
+    FrameParams f = fp;
+    BinSource bin = in;
+    int nn = n;
+    RegionOps ro{};
+    int rb = 0;
+    PendingFold cur;
+    cur.active = true; cur.sc = sc; cur.src = fsrc; cur.geom = m->geom; cur.n = n;
+    if (!pipelined || !m->pend.active) {
+        // nothing in flight: the bin kernel carries the deferred region operations in spare blocks
+        if ((rc = take_region_ops(m, ro, rb))) return rc;
+        cudaStream_t st_bin = m->stream;
+        if (pipelined && m->pipe_mode == 1) { // later bins of the pipeline run on the front stream: order it behind everything issued so far
+            GEM_CUDA(m, cudaEventRecord(m->ev_mark, m->stream));
+            GEM_CUDA(m, cudaStreamWaitEvent(m->front_stream, m->ev_mark, 0));
+            st_bin = m->front_stream;
+        }
+        GEM_LAUNCH_ON(m, st_bin, GEM_PROF_TRANSFORM_BIN, bk<<<pb + rb, ADD_BLOCK, 0, st_bin>>>(g, ml, f, bin, nn, sc, ro, pb, st, frames));
+        GEM_CUDA(m, cudaGetLastError());
+        commit_region_ops(m);
+        if (pipelined && m->pipe_mode == 1) GEM_CUDA(m, cudaEventRecord(m->ev_bin[par], st_bin));
+        if (!pipelined) {
+            RegionOps none{};
+            if ((rc = launch_fold(m, m->stream, cur, none, 0, do_fuse, do_lowest))) return rc;
+        } else {
+            m->pend = cur;
+        }
+    } else {
+        // steady state of the pipeline
+        if ((rc = take_region_ops(m, ro, rb))) return rc; // row / column clears of this call's Move: executed by the previous call's fold launch
+        PendingFold prev = m->pend;
+        const int fb = blocks_for((size_t)prev.n, ADD_BLOCK, 148 * 8);
+        RegionOps none{};
+        if (m->pipe_mode == 2) {
+            int pbk = pb, one = 1, fbk = fb;
+            void *bin_args[] = {&g, &ml, &f, &bin, &nn, &sc, &none, &pbk, &st, (void *)&frames};
+            void *fold_args[] = {&prev.geom, &ml, &prev.sc, &prev.src, &ro, &fbk, &one, &one};
+            if ((rc = launch_frame_graph(m, bk, bin_args, pb, fold_args, fb + rb))) return rc;
+        } else {
+            GEM_CUDA(m, cudaStreamWaitEvent(m->front_stream, m->ev_fold[par], 0)); // the fold that last used this parity's scratch
+            GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_TRANSFORM_BIN, bk<<<pb, ADD_BLOCK, 0, m->front_stream>>>(g, ml, f, bin, nn, sc, none, pb, st, frames));
+            GEM_CUDA(m, cudaEventRecord(m->ev_bin[par], m->front_stream));
+            GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_bin[prev.sc.par], 0));
+            if ((rc = launch_fold(m, m->stream, prev, ro, rb, true, true))) return rc;
+            GEM_CUDA(m, cudaEventRecord(m->ev_fold[prev.sc.par], m->stream));
+        }
+        commit_region_ops(m);
+        m->pend = cur;
+    }
+    m->ctr_last = sc.ctr;
+    m->call_no++;
+    return GEM_OK;
 }
 
 } // namespace
@@ -513,8 +614,13 @@ int gem_create(const gem_config *cfg, gem_map **out)
     m->geom.cols = tiled ? cfg->tile_cols : m->L;
     m->nc = (size_t)m->geom.rows * m->geom.cols;
     m->P = cfg->max_points > 0 ? cfg->max_points : (1 << 21);
-    if (m->P > (1 << 22)) m->P = 1 << 22; // the fold's sort key packs the point index into 22 bits
-    if ((size_t)m->P < m->nc / 32 + 1) m->P = (int)(m->nc / 32 + 1); // per-point scratch doubles as the ray bitmap
+    // the fold's sort key packs the point index of a launch into 22 bits; larger calls are chunked
+    if (m->P > (1 << FOLD_INDEX_BITS)) m->P = 1 << FOLD_INDEX_BITS;
+    {
+        const char *env = getenv("GEM_B200_PIPE"); // graph (default) | stream | off
+        if (env && !strcmp(env, "stream")) m->pipe_mode = 1;
+        else if (env && !strcmp(env, "off")) m->pipe_mode = 0;
+    }
 
     int rc = GEM_OK;
     auto bail = [&](int code) {
@@ -530,29 +636,33 @@ int gem_create(const gem_config *cfg, gem_map **out)
         if (e != cudaSuccess) { m->err = cudaGetErrorString(e); return bail(GEM_ERR_CUDA); }
         m->own_stream = true;
     }
-    const size_t nc = m->nc, P = (size_t)m->P;
-    if ((rc = dev_alloc(m, &m->ml.ev, nc)) || (rc = dev_alloc(m, &m->ml.ci, nc)) ||
-        (rc = dev_alloc(m, &m->ml.traver, nc)) || (rc = dev_alloc(m, &m->ml.lowest, nc)) ||
-        (rc = dev_alloc(m, &m->ml.rough, nc)) || (rc = dev_alloc(m, &m->ml.slope, nc)) ||
-        (rc = dev_alloc(m, &m->ml.traver_out, nc)) || (rc = dev_alloc(m, &m->sc.cnt, nc)) ||
-        (rc = dev_alloc(m, &m->sc.cellBase, nc)) || (rc = dev_alloc(m, &m->sc.touched, P < nc ? P : nc)) ||
-        (rc = dev_alloc(m, &m->ctr_buf[0], 2)) || (rc = dev_alloc(m, &m->sc.key, P)) ||
-        (rc = dev_alloc(m, &m->sc.tsmall, P < nc ? P : nc)) || (rc = dev_alloc(m, &m->sc.tlarge, list_cap(P, nc, FOLD_SMALL_K))) || (rc = dev_alloc(m, &m->sc.tlong, list_cap(P, nc, FOLD_LONG_K))) ||
-        (rc = dev_alloc(m, &m->sc.rank, P)) || (rc = dev_alloc(m, &m->sc.h, P)) ||
-        (rc = dev_alloc(m, &m->sc.hv, P)) || (rc = dev_alloc(m, &m->sc.recA, P)) ||
-        (rc = dev_alloc(m, &m->sc.recI, P)))
+    const size_t nc = m->nc, P = (size_t)m->P, T = P < nc ? P : nc;
+    if ((rc = dev_alloc(m, &m->ml.cell, nc)) || (rc = dev_alloc(m, &m->ml.traver, nc)) || (rc = dev_alloc(m, &m->ml.lowest, nc)) ||
+        (rc = dev_alloc(m, &m->ml.rough, nc)) || (rc = dev_alloc(m, &m->ml.slope, nc)) || (rc = dev_alloc(m, &m->ml.traver_out, nc)) ||
+        (rc = dev_alloc(m, &m->ctr[0], 3)))
         return bail(rc);
-    e = cudaHostAlloc((void **)&m->h_ctr, sizeof(Counters), cudaHostAllocDefault);
+    for (int i = 1; i < 3; i++) m->ctr[i] = m->ctr[0] + i;
+    m->ctr_last = m->ctr[0];
+    for (int p = 0; p < 2; p++) {
+        BinScratch &sc = m->bs[p];
+        sc.par = p;
+        // every cell with k >= 9 records takes at most 4k + 8 pool slots (chunks of 32, 128, ... records + headers)
+        sc.pool_cap = (int)std::min<size_t>(5 * P + 64, (size_t)0x7ffffff0);
+        if ((rc = dev_alloc(m, &sc.touched, T)) || (rc = dev_alloc(m, &sc.chunk0, (size_t)CHUNK0 * T)) || (rc = dev_alloc(m, &sc.ovf1, T)) ||
+            (rc = dev_alloc(m, &sc.pool, (size_t)sc.pool_cap + 1)) || (rc = dev_alloc(m, &sc.tlarge, list_cap(P, nc, CHUNK0))) ||
+            (rc = dev_alloc(m, &sc.tlong, list_cap(P, nc, FOLD_LONG_FROM))))
+            return bail(rc);
+        e = cudaMemsetAsync(sc.ovf1, 0, T * sizeof(int), m->stream);
+        if (e != cudaSuccess) { m->err = cudaGetErrorString(e); return bail(GEM_ERR_CUDA); }
+    }
+    e = cudaHostAlloc((void **)&m->h_ctr, sizeof(BinCounters), cudaHostAllocDefault);
     if (e != cudaSuccess) { m->err = cudaGetErrorString(e); return bail(GEM_ERR_CUDA); }
     // G_Init_map gpu.cu:198-214
     GEM_LAUNCH(m, GEM_PROF_CLEAR, k_clear_range<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml, 0, nc, 2));
     GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.rough, nc, 0.0f));
     GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.slope, nc, 0.0f));
     GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(nc, 256), 256, 0, m->stream>>>(m->ml.traver_out, nc, -10.0f));
-    e = cudaMemsetAsync(m->sc.cnt, 0, nc * sizeof(int), m->stream);
-    m->ctr_buf[1] = m->ctr_buf[0] + 1;
-    m->ctr_last = m->ctr_buf[0];
-    if (e == cudaSuccess) e = cudaMemsetAsync(m->ctr_buf[0], 0, 2 * sizeof(Counters), m->stream);
+    e = cudaMemsetAsync(m->ctr[0], 0, 3 * sizeof(BinCounters), m->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
     if (e != cudaSuccess) {
@@ -560,26 +670,6 @@ int gem_create(const gem_config *cfg, gem_map **out)
         return bail(GEM_ERR_NO_DEVICE);
     }
     pend_all_floor(m); // first Fuse floors every cell (gpu.cu:533-534)
-    {   // the fused add kernel needs a co-resident grid (cooperative launch)
-        int coop = 0, per_sm = 0;
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_add_fused<IN_XYZI, ATTR_XYZI>, ADD_BLOCK, 0) == cudaSuccess)
-            m->coop_blocks = per_sm * prop.multiProcessorCount;
-        // measured on B200 (profiles/): four stream-ordered launches (32.8 us/frame) beat the
-        // single cooperative launch with three grid barriers (36.5 us/frame), so the fused
-        // kernel is opt-in
-        const char *env = getenv("GEM_B200_FUSED");
-        if (!(env && atoi(env) == 1)) m->coop_blocks = 0;
-        // measured on B200: with PDL the frame takes 101 us instead of 32.9 us (waiting dependent
-        // CTAs occupy the SMs the predecessor's serial fold tail needs), so it is opt-in
-        const char *envp = getenv("GEM_B200_PDL");
-        if (envp && atoi(envp) == 1) m->pdl = true;
-        const char *envf = getenv("GEM_B200_PDL_FRONT");
-        if (envf && atoi(envf) == 1) m->pdl_front = true;
-        const char *envn = getenv("GEM_B200_FUSED_MAX_POINTS");
-        if (envn && atoi(envn) > 0) m->fused_max_points = atoi(envn);
-        cudaGetLastError();
-    }
     *out = m;
     return GEM_OK;
 }
@@ -587,56 +677,56 @@ int gem_create(const gem_config *cfg, gem_map **out)
 int gem_destroy(gem_map *m)
 {
     if (!m) return GEM_OK;
-    SetDev sd(m->dev);
-    if (m->stream) cudaStreamSynchronize(m->stream);
-    for (auto &sp : m->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
-    for (cudaEvent_t e : m->free_events) cudaEventDestroy(e);
-    for (void *p : m->allocs) cudaFree(p);
-    if (m->h_ctr) cudaFreeHost(m->h_ctr);
-    if (m->h_ctr_ring) cudaFreeHost(m->h_ctr_ring);
-    if (m->h_frames) cudaFreeHost(m->h_frames);
-    for (int i = 0; i < 3; i++) {
-        if (m->ev_bin[i]) cudaEventDestroy(m->ev_bin[i]);
-        if (m->ev_front[i]) cudaEventDestroy(m->ev_front[i]);
-        if (m->ev_fold[i]) cudaEventDestroy(m->ev_fold[i]);
+    {
+        Lock lk(m->mu);
+        SetDev sd(m->dev);
+        if (m->front_stream) cudaStreamSynchronize(m->front_stream);
+        if (m->stream) cudaStreamSynchronize(m->stream);
+        for (auto &kv : m->graphs) {
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+            if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+        }
+        for (auto &sp : m->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+        for (cudaEvent_t e : m->free_events) cudaEventDestroy(e);
+        for (void *p : m->allocs) cudaFree(p);
+        if (m->h_ctr) cudaFreeHost(m->h_ctr);
+        if (m->h_ctr_ring) cudaFreeHost(m->h_ctr_ring);
+        if (m->h_frames) cudaFreeHost(m->h_frames);
+        for (int i = 0; i < 2; i++) {
+            if (m->ev_bin[i]) cudaEventDestroy(m->ev_bin[i]);
+            if (m->ev_fold[i]) cudaEventDestroy(m->ev_fold[i]);
+        }
+        if (m->ev_mark) cudaEventDestroy(m->ev_mark);
+        if (m->front_stream) cudaStreamDestroy(m->front_stream);
+        for (int i = 0; i < 4; i++) if (m->ev_frames[i]) cudaEventDestroy(m->ev_frames[i]);
+        for (int i = 0; i < 3; i++) {
+            if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
+            if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
+        }
+        if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); }
+        if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
     }
-    if (m->front_stream) { cudaStreamSynchronize(m->front_stream); cudaStreamDestroy(m->front_stream); }
-    if (m->mid_owned && m->mid_stream) { cudaStreamSynchronize(m->mid_stream); cudaStreamDestroy(m->mid_stream); }
-    for (int i = 0; i < 4; i++) if (m->ev_frames[i]) cudaEventDestroy(m->ev_frames[i]);
-    for (int i = 0; i < 2; i++) {
-        if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
-        if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
-    }
-    if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); }
-    if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return GEM_OK;
 }
 
 void *gem_get_stream(gem_map *m) { return m ? (void *)m->stream : nullptr; }
 
-int gem_debug_phase_stamps(gem_map *m, int enable, unsigned long long out[16])
+int gem_flush(gem_map *m)
 {
     if (!m) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
     SetDev sd(m->dev);
-    if (enable && !m->sc.tstamp) {
-        int rc = dev_alloc(m, &m->sc.tstamp, 16);
-        if (rc) return rc;
-        GEM_CUDA(m, cudaMemsetAsync(m->sc.tstamp, 0, 16 * 8, m->stream));
-    }
-    if (out && m->sc.tstamp) {
-        GEM_CUDA(m, cudaMemcpyAsync(out, m->sc.tstamp, 16 * 8, cudaMemcpyDeviceToHost, m->stream));
-        GEM_CUDA(m, cudaStreamSynchronize(m->stream));
-        GEM_CUDA(m, cudaMemsetAsync(m->sc.tstamp, 0, 16 * 8, m->stream));
-        GEM_CUDA(m, cudaStreamSynchronize(m->stream));
-    }
-    return GEM_OK;
+    return drain(m);
 }
 
 int gem_sync(gem_map *m)
 {
     if (!m) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
     SetDev sd(m->dev);
+    int rc = drain(m);
+    if (rc) return rc;
     GEM_CUDA(m, cudaStreamSynchronize(m->stream));
     return GEM_OK;
 }
@@ -668,6 +758,7 @@ static void clear_cols(gem_map *m, int start, int n) { m->pending.push_back(Regi
 int gem_move(gem_map *m, const float pos[3], float centre_out[2], int start_out[2], float shift_out[2])
 {
     if (!m || !pos) return fail(m, GEM_ERR_INVALID, "gem_move: null argument");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     const int L = m->L;
     m->sensorZ = pos[2]; // gpu.cu:1011-1012
@@ -692,6 +783,7 @@ int gem_move(gem_map *m, const float pos[3], float centre_out[2], int start_out[
             // |shift| >= L clears everything (the reference tests only the positive side,
             // gpu.cu:1033, and would write out of bounds for shift <= -L)
             if (indexShift[i] >= L || indexShift[i] <= -L) {
+                { int rcd = drain(m); if (rcd) return rcd; }
                 GEM_LAUNCH(m, GEM_PROF_CLEAR, k_clear_range<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, 0, m->nc, 1));
                 pend_all_floor(m);
             } else {
@@ -722,10 +814,20 @@ int gem_move(gem_map *m, const float pos[3], float centre_out[2], int start_out[
     return GEM_OK;
 }
 
+
 // ---- fused add -------------------------------------------------------------------------------
+static BinSource xyzi_source(const void *xyzi, const void *rgba, int off)
+{
+    BinSource in{};
+    in.xyzi = (const float4 *)xyzi + off;
+    in.rgba = rgba ? (const uchar4 *)rgba + off : nullptr;
+    return in;
+}
+
 int gem_add_points(gem_map *m, const void *xyzi, const void *rgba, int n, const gem_frame *frame)
 {
     if (!m || !frame || n < 0 || (n > 0 && !xyzi)) return fail(m, GEM_ERR_INVALID, "gem_add_points: bad argument");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = GEM_OK;
     const FrameParams fp = make_frame(frame);
@@ -733,13 +835,9 @@ int gem_add_points(gem_map *m, const void *xyzi, const void *rgba, int n, const 
     if (n == 0) return flush_all_pending(m);
     for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
-        PointInput in{};
-        in.xyzi = (const float4 *)xyzi + off;
-        in.rgba = rgba ? (const uchar4 *)rgba + off : nullptr;
-        AttrInput a{};
-        a.xyzi = in.xyzi;
-        a.rgba = in.rgba;
-        if ((rc = add_chunk<IN_XYZI, ATTR_XYZI>(m, in, a, cn, fp))) return rc;
+        const BinSource in = xyzi_source(xyzi, rgba, off);
+        const FoldSrc fs{SRC_XYZI, in.xyzi};
+        if ((rc = enqueue_add<SRC_XYZI>(m, in, fs, cn, fp, nullptr, nullptr, false, true, true))) return rc;
         if (n > m->P && (rc = read_counters(m, cn, true))) return rc; // chunked: keep totals
     }
     if (n <= m->P) m->stats.points_in = n; // counters are fetched lazily by gem_get_stats
@@ -749,63 +847,24 @@ int gem_add_points(gem_map *m, const void *xyzi, const void *rgba, int n, const 
 int gem_add_points_host(gem_map *m, const void *xyzi, const void *rgba, int n, const gem_frame *frame)
 {
     if (!m || !frame || n < 0 || (n > 0 && !xyzi)) return fail(m, GEM_ERR_INVALID, "gem_add_points_host: bad argument");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = ensure_host_staging(m);
     if (rc) return rc;
     const FrameParams fp = make_frame(frame);
     memset(&m->stats, 0, sizeof m->stats);
     if (n == 0) { if ((rc = flush_all_pending(m))) return rc; return gem_sync(m); }
+    if ((rc = drain(m))) return rc; // the staging buffers may still feed a deferred fold
     for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
-        if (cn > 0) {
-            GEM_CUDA(m, cudaMemcpyAsync(m->d_xyzi, (const float4 *)xyzi + off, (size_t)cn * 16, cudaMemcpyHostToDevice, m->stream));
-            if (rgba)
-                GEM_CUDA(m, cudaMemcpyAsync(m->d_rgba, (const uchar4 *)rgba + off, (size_t)cn * 4, cudaMemcpyHostToDevice, m->stream));
-        }
-        PointInput in{};
-        in.xyzi = (const float4 *)m->d_xyzi;
-        in.rgba = rgba ? (const uchar4 *)m->d_rgba : nullptr;
-        AttrInput a{};
-        a.xyzi = in.xyzi;
-        a.rgba = in.rgba;
-        if ((rc = add_chunk<IN_XYZI, ATTR_XYZI>(m, in, a, cn, fp))) return rc;
+        GEM_CUDA(m, cudaMemcpyAsync(m->d_xyzi, (const float4 *)xyzi + off, (size_t)cn * 16, cudaMemcpyHostToDevice, m->stream));
+        if (rgba)
+            GEM_CUDA(m, cudaMemcpyAsync(m->d_rgba, (const uchar4 *)rgba + off, (size_t)cn * 4, cudaMemcpyHostToDevice, m->stream));
+        const BinSource in = xyzi_source(m->d_xyzi, rgba ? m->d_rgba : nullptr, 0);
+        const FoldSrc fs{SRC_XYZI, in.xyzi};
+        if ((rc = enqueue_add<SRC_XYZI>(m, in, fs, cn, fp, nullptr, nullptr, false, true, true))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc; // also the host-visible completion point
     }
-    return GEM_OK;
-}
-
-static int pipe_setup(gem_map *m)
-{
-    if (m->pipe_ready) return GEM_OK;
-    int rc;
-    const size_t nc = m->nc, P = (size_t)m->P, T = P < nc ? P : nc;
-    for (int i = 0; i < 3; i++) {
-        Scratch &sc = m->pipe_sc[i];
-        memset(&sc, 0, sizeof sc);
-        if ((rc = dev_alloc(m, &sc.cnt, nc)) || (rc = dev_alloc(m, &sc.cellBase, nc)) || (rc = dev_alloc(m, &sc.touched, T)) ||
-            (rc = dev_alloc(m, &sc.tsmall, T)) || (rc = dev_alloc(m, &sc.tlarge, list_cap(P, nc, FOLD_SMALL_K))) || (rc = dev_alloc(m, &sc.tlong, list_cap(P, nc, FOLD_LONG_K))) ||
-            (rc = dev_alloc(m, &sc.key, P)) || (rc = dev_alloc(m, &sc.rank, P)) || (rc = dev_alloc(m, &sc.h, P)) ||
-            (rc = dev_alloc(m, &sc.hv, P)) || (rc = dev_alloc(m, &sc.recA, P)) || (rc = dev_alloc(m, &sc.recI, P)))
-            return rc;
-        GEM_CUDA(m, cudaMemsetAsync(sc.cnt, 0, nc * sizeof(int), m->stream));
-        GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_bin[i], cudaEventDisableTiming));
-        GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_front[i], cudaEventDisableTiming));
-        GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_fold[i], cudaEventDisableTiming));
-    }
-    if ((rc = dev_alloc(m, &m->pipe_ctr[0], 4))) return rc;
-    for (int i = 1; i < 4; i++) m->pipe_ctr[i] = m->pipe_ctr[0] + i;
-    GEM_CUDA(m, cudaMemsetAsync(m->pipe_ctr[0], 0, 4 * sizeof(Counters), m->stream));
-    GEM_CUDA(m, cudaStreamCreateWithFlags(&m->front_stream, cudaStreamNonBlocking));
-    {   // GEM_B200_STREAM_STAGES=2 keeps alloc+scatter on the transform stream (the two-stage pipeline)
-        const char *env = getenv("GEM_B200_STREAM_STAGES");
-        if (env && atoi(env) == 2) m->mid_stream = m->front_stream;
-        else {
-            GEM_CUDA(m, cudaStreamCreateWithFlags(&m->mid_stream, cudaStreamNonBlocking));
-            m->mid_owned = true;
-        }
-    }
-    for (int i = 0; i < 3; i++) GEM_CUDA(m, cudaEventRecord(m->ev_fold[i], m->stream)); // sets are free once init is done
-    m->pipe_ready = true;
     return GEM_OK;
 }
 
@@ -813,47 +872,14 @@ int gem_add_points_stream(gem_map *m, const void *xyzi, const void *rgba, int n,
 {
     if (!m || !frame || n < 0 || (n > 0 && !xyzi)) return fail(m, GEM_ERR_INVALID, "gem_add_points_stream: bad argument");
     if (n > m->P) return fail(m, GEM_ERR_INVALID, "gem_add_points_stream: n exceeds max_points (use gem_add_points)");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
-    int rc = pipe_setup(m);
-    if (rc) return rc;
     if (n == 0) return flush_all_pending(m);
-    const unsigned i = m->pipe_calls++;
-    const int par = (int)(i % 3u), c = (int)(i & 3u);
-    Scratch sc = m->pipe_sc[par];
-    sc.ctr = m->pipe_ctr[c];
-    sc.ctr_next = m->pipe_ctr[(c + 1) & 3];
-    sc.tstamp = nullptr;
     const FrameParams fp = make_frame(frame);
-    PointInput in{};
-    in.xyzi = (const float4 *)xyzi;
-    in.rgba = (const uchar4 *)rgba;
-    AttrInput a{};
-    a.xyzi = in.xyzi;
-    a.rgba = in.rgba;
-    // stage 1 (front stream): transform+bin of THIS frame -- overlaps alloc+scatter of the previous frame and the
-    // fold of the one before; it only waits for the fold that last used this scratch set (three calls ago)
-    GEM_CUDA(m, cudaStreamWaitEvent(m->front_stream, m->ev_fold[par], 0));
-    RegionOps none{};
-    const int pb = blocks_for((size_t)n, ADD_BLOCK, 148 * 16);
-    GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_TRANSFORM_BIN,
-                  k_transform_bin<IN_XYZI><<<pb, ADD_BLOCK, 0, m->front_stream>>>(m->geom, m->ml, fp, in, n, sc, none, pb, nullptr, nullptr));
-    // stage 2 (mid stream): alloc + scatter
-    if (m->mid_stream != m->front_stream) {
-        GEM_CUDA(m, cudaEventRecord(m->ev_bin[par], m->front_stream));
-        GEM_CUDA(m, cudaStreamWaitEvent(m->mid_stream, m->ev_bin[par], 0));
-    }
-    GEM_LAUNCH_ON(m, m->mid_stream, GEM_PROF_ALLOC,
-                  launch_pdl(m->pdl_front, k_alloc_cells, blocks_for((size_t)n, ADD_BLOCK, 148 * 4), ADD_BLOCK, m->mid_stream, sc));
-    GEM_LAUNCH_ON(m, m->mid_stream, GEM_PROF_SCATTER,
-                  launch_pdl(m->pdl_front, k_scatter<ATTR_XYZI, 1>, blocks_for((size_t)n, ADD_BLOCK, 148 * 16), ADD_BLOCK, m->mid_stream, a, n, sc));
-    GEM_CUDA(m, cudaEventRecord(m->ev_front[par], m->mid_stream));
-    // stage 3 (main stream): deferred scroll clears / floors, then the fold (the only kernel that touches the layers)
-    if (!m->pending.empty() && (rc = flush_all_pending(m))) return rc;
-    GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_front[par], 0));
-    GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<blocks_for((size_t)n, ADD_BLOCK, 148 * 8), ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, sc, 1, 1));
-    GEM_CUDA(m, cudaEventRecord(m->ev_fold[par], m->stream));
-    GEM_CUDA(m, cudaGetLastError());
-    m->ctr_last = m->pipe_ctr[c];
+    const BinSource in = xyzi_source(xyzi, rgba, 0);
+    const FoldSrc fs{SRC_XYZI, in.xyzi};
+    int rc = enqueue_add<SRC_XYZI>(m, in, fs, n, fp, nullptr, nullptr, true, true, true);
+    if (rc) return rc;
     memset(&m->stats, 0, sizeof m->stats);
     m->stats.points_in = n;
     return GEM_OK;
@@ -868,13 +894,13 @@ int gem_add_points_multi(gem_map *m, const void *xyzi, const void *rgba, int n_s
     if (offsets[0] != 0 || n < 0 || n > m->P) return fail(m, GEM_ERR_INVALID, "gem_add_points_multi: offsets must start at 0 and n <= max_points");
     for (int s = 0; s < n_segments; s++)
         if (offsets[s + 1] < offsets[s]) return fail(m, GEM_ERR_INVALID, "gem_add_points_multi: offsets not monotone");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = GEM_OK;
-    if (!m->h_frames) {
-        GEM_CUDA(m, cudaHostAlloc((void **)&m->h_frames, 4 * MAX_SEGMENTS * sizeof(FrameParams), cudaHostAllocDefault));
-        if ((rc = dev_alloc(m, &m->d_frames, (size_t)4 * MAX_SEGMENTS))) return rc;
-        for (int i = 0; i < 4; i++) GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_frames[i], cudaEventDisableTiming));
-    }
+    if (!m->h_frames) GEM_CUDA(m, cudaHostAlloc((void **)&m->h_frames, 4 * MAX_SEGMENTS * sizeof(FrameParams), cudaHostAllocDefault));
+    if (!m->d_frames && (rc = dev_alloc(m, &m->d_frames, (size_t)4 * MAX_SEGMENTS))) return rc;
+    for (int i = 0; i < 4; i++)
+        if (!m->ev_frames[i]) GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_frames[i], cudaEventDisableTiming));
     if (n == 0) return flush_all_pending(m);
     const int slot = (int)(m->multi_calls++ & 3u);
     if (m->multi_calls > 4) GEM_CUDA(m, cudaEventSynchronize(m->ev_frames[slot])); // pinned slot free again
@@ -885,22 +911,10 @@ int gem_add_points_multi(gem_map *m, const void *xyzi, const void *rgba, int n_s
     for (int s = 0; s < n_segments; s++) hf[s] = make_frame(&frames[s]);
     GEM_CUDA(m, cudaMemcpyAsync(df, hf, (size_t)n_segments * sizeof(FrameParams), cudaMemcpyHostToDevice, m->stream));
     GEM_CUDA(m, cudaEventRecord(m->ev_frames[slot], m->stream));
-    RegionOps ro;
-    int rb = 0;
-    if ((rc = take_region_ops(m, ro, rb))) return rc;
-    const Scratch sc = cur_scratch(m);
-    PointInput in{};
-    in.xyzi = (const float4 *)xyzi;
-    in.rgba = (const uchar4 *)rgba;
-    AttrInput a{};
-    a.xyzi = in.xyzi;
-    a.rgba = in.rgba;
-    const int U = points_per_thread(n);
-    const int pb = blocks_for((size_t)(n + U - 1) / U, ADD_BLOCK, 148 * 32);
-    if (U == 4) GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin_multi<4><<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, st, df, in, n, sc, ro, pb));
-    else if (U == 2) GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin_multi<2><<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, st, df, in, n, sc, ro, pb));
-    else GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin_multi<1><<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, st, df, in, n, sc, ro, pb));
-    if ((rc = run_group_fold<ATTR_XYZI>(m, sc, a, n, true, true))) return rc;
+    const BinSource in = xyzi_source(xyzi, rgba, 0);
+    const FoldSrc fs{SRC_XYZI, in.xyzi};
+    // pipelined like gem_add_points_stream: consecutive multi-sensor steps overlap bin(i+1) with fold(i)
+    if ((rc = enqueue_add<SRC_XYZI>(m, in, fs, n, hf[0], &st, df, true, true, true))) return rc;
     memset(&m->stats, 0, sizeof m->stats);
     m->stats.points_in = n;
     return GEM_OK;
@@ -910,38 +924,43 @@ int gem_add_points_host_async(gem_map *m, const void *xyzi, const void *rgba, in
 {
     if (!m || !frame || n < 0 || (n > 0 && !xyzi)) return fail(m, GEM_ERR_INVALID, "gem_add_points_host_async: bad argument");
     if (n > m->P) return fail(m, GEM_ERR_INVALID, "gem_add_points_host_async: n exceeds max_points (use gem_add_points_host)");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = GEM_OK;
-    if (!m->copy_stream) { // lazy set-up: copy stream, two staging sets, events, counter ring
-        GEM_CUDA(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            if ((rc = dev_alloc(m, (float4 **)&m->d_axyzi[i], (size_t)m->P))) return rc;
-            if ((rc = dev_alloc(m, (uchar4 **)&m->d_argba[i], (size_t)m->P))) return rc;
-            GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+    // lazy set-up (every handle created at most once, also after a partial failure): copy stream, three staging
+    // sets, events, counter ring
+    if (!m->copy_stream) GEM_CUDA(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++) {
+        if (!m->d_axyzi[i] && (rc = dev_alloc(m, (float4 **)&m->d_axyzi[i], (size_t)m->P))) return rc;
+        if (!m->d_argba[i] && (rc = dev_alloc(m, (uchar4 **)&m->d_argba[i], (size_t)m->P))) return rc;
+        if (!m->ev_h2d[i]) GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+        if (!m->ev_done[i]) {
             GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
             GEM_CUDA(m, cudaEventRecord(m->ev_done[i], m->stream));
         }
-        GEM_CUDA(m, cudaHostAlloc((void **)&m->h_ctr_ring, 2 * sizeof(Counters), cudaHostAllocDefault));
     }
+    if (!m->h_ctr_ring) GEM_CUDA(m, cudaHostAlloc((void **)&m->h_ctr_ring, 2 * sizeof(BinCounters), cudaHostAllocDefault));
     if (n == 0) return flush_all_pending(m);
-    const int b = (int)(m->async_calls++ & 1u);
-    // copy stream: wait until the kernels that last read staging set b are done, then H2D
+    const unsigned i = m->async_calls++;
+    const int b = (int)(i % 3u);
+    // copy stream: wait until the fold that last read staging set b (call i-3) has been issued and is done, then H2D
     GEM_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->ev_done[b], 0));
     GEM_CUDA(m, cudaMemcpyAsync(m->d_axyzi[b], xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, m->copy_stream));
     if (rgba) GEM_CUDA(m, cudaMemcpyAsync(m->d_argba[b], rgba, (size_t)n * 4, cudaMemcpyHostToDevice, m->copy_stream));
     GEM_CUDA(m, cudaEventRecord(m->ev_h2d[b], m->copy_stream));
-    // compute stream: wait for the copy, run the add, read the counters back, mark set b free
+    // compute stream: wait for the copy, issue {fold of the previous call || bin of this one}
     GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_h2d[b], 0));
+    if (m->pipe_mode == 1 && m->front_stream) GEM_CUDA(m, cudaStreamWaitEvent(m->front_stream, m->ev_h2d[b], 0));
     const FrameParams fp = make_frame(frame);
-    PointInput in{};
-    in.xyzi = (const float4 *)m->d_axyzi[b];
-    in.rgba = rgba ? (const uchar4 *)m->d_argba[b] : nullptr;
-    AttrInput a{};
-    a.xyzi = in.xyzi;
-    a.rgba = in.rgba;
-    if ((rc = add_chunk<IN_XYZI, ATTR_XYZI>(m, in, a, n, fp))) return rc;
-    GEM_CUDA(m, cudaMemcpyAsync(&m->h_ctr_ring[b], m->ctr_last, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
-    GEM_CUDA(m, cudaEventRecord(m->ev_done[b], m->stream));
+    const BinSource in = xyzi_source(m->d_axyzi[b], rgba ? m->d_argba[b] : nullptr, 0);
+    const FoldSrc fs{SRC_XYZI, in.xyzi};
+    BinCounters *prev_ctr = m->pend.active ? m->pend.sc.ctr : nullptr;
+    if ((rc = enqueue_add<SRC_XYZI>(m, in, fs, n, fp, nullptr, nullptr, true, true, true))) return rc;
+    // the step's host-visible result: the counters of the newest call whose fold has been issued
+    GEM_CUDA(m, cudaMemcpyAsync(&m->h_ctr_ring[i & 1u], prev_ctr ? prev_ctr : m->ctr_last, sizeof(BinCounters), cudaMemcpyDeviceToHost, m->stream));
+    // staging set (i-1) % 3 was last read by the fold just issued (or by this call's own fold in the serial fallback)
+    GEM_CUDA(m, cudaEventRecord(m->ev_done[(i + 2u) % 3u], m->stream));
+    if (!m->pend.active) GEM_CUDA(m, cudaEventRecord(m->ev_done[b], m->stream));
     memset(&m->stats, 0, sizeof m->stats);
     m->stats.points_in = n; // the rest is fetched by gem_get_stats
     return GEM_OK;
@@ -950,21 +969,21 @@ int gem_add_points_host_async(gem_map *m, const void *xyzi, const void *rgba, in
 int gem_add_cloud_pcl_host(gem_map *m, const void *pts, int n, const gem_frame *frame)
 {
     if (!m || !frame || n < 0 || (n > 0 && !pts)) return fail(m, GEM_ERR_INVALID, "gem_add_cloud_pcl_host: bad argument");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = ensure_pcl_staging(m);
     if (rc) return rc;
     const FrameParams fp = make_frame(frame);
     memset(&m->stats, 0, sizeof m->stats);
     if (n == 0) { if ((rc = flush_all_pending(m))) return rc; return gem_sync(m); }
+    if ((rc = drain(m))) return rc;
     for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
-        if (cn > 0)
-            GEM_CUDA(m, cudaMemcpyAsync(m->d_pcl, (const char *)pts + (size_t)off * 32, (size_t)cn * 32, cudaMemcpyHostToDevice, m->stream));
-        PointInput in{};
+        GEM_CUDA(m, cudaMemcpyAsync(m->d_pcl, (const char *)pts + (size_t)off * 32, (size_t)cn * 32, cudaMemcpyHostToDevice, m->stream));
+        BinSource in{};
         in.pcl = (const float4 *)m->d_pcl;
-        AttrInput a{};
-        a.pcl = in.pcl;
-        if ((rc = add_chunk<IN_PCL32, ATTR_PCL32>(m, in, a, cn, fp))) return rc;
+        const FoldSrc fs{SRC_PCL32, in.pcl};
+        if ((rc = enqueue_add<SRC_PCL32>(m, in, fs, cn, fp, nullptr, nullptr, false, true, true))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc;
     }
     return GEM_OK;
@@ -977,66 +996,69 @@ int gem_process_points(gem_map *m, int *map_index, const float *x, const float *
     if (!m || !frame || n < 0 || (n > 0 && (!x || !y || !z)))
         return fail(m, GEM_ERR_INVALID, "gem_process_points: bad argument");
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_process_points: not available on tiled handles");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = ensure_compat_staging(m);
     if (rc) return rc;
     const FrameParams fp = make_frame(frame);
     memset(&m->stats, 0, sizeof m->stats);
-    for (int off = 0; off < n; off += m->P) {
+    if ((rc = drain(m))) return rc;
+    // Process_points does not fuse: clears/floors stay pending (they are handed to the bin kernel only by fusing calls)
+    std::vector<RegionOp> keep;
+    keep.swap(m->pending);
+    for (int off = 0; off < n && rc == GEM_OK; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
         const size_t b = (size_t)cn * 4;
-        GEM_CUDA(m, cudaMemcpyAsync(m->d_x, x + off, b, cudaMemcpyHostToDevice, m->stream));
-        GEM_CUDA(m, cudaMemcpyAsync(m->d_y, y + off, b, cudaMemcpyHostToDevice, m->stream));
-        GEM_CUDA(m, cudaMemcpyAsync(m->d_z, z + off, b, cudaMemcpyHostToDevice, m->stream));
-        PointInput in{};
+        cudaError_t e = cudaMemcpyAsync(m->d_x, x + off, b, cudaMemcpyHostToDevice, m->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_y, y + off, b, cudaMemcpyHostToDevice, m->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_z, z + off, b, cudaMemcpyHostToDevice, m->stream);
+        if (e != cudaSuccess) { rc = fail(m, GEM_ERR_CUDA, cudaGetErrorString(e)); break; }
+        BinSource in{};
         in.x = m->d_x; in.y = m->d_y; in.z = m->d_z;
-        const Scratch sc = cur_scratch(m);
-        RegionOps ro{}; // Process_points does not fuse: clears/floors stay pending
-        const int pb = blocks_for((size_t)cn, ADD_BLOCK, 148 * 16);
-        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_transform_bin<IN_SOA><<<pb, ADD_BLOCK, 0, m->stream>>>(
-            m->geom, m->ml, fp, in, cn, sc, ro, pb, m->d_xt, m->d_yt));
-        AttrInput a{};
-        if ((rc = run_group_fold<ATTR_NONE>(m, sc, a, cn, false, true))) return rc; // lowest-scan only
-        if (map_index) GEM_CUDA(m, cudaMemcpyAsync(map_index + off, m->sc.key, b, cudaMemcpyDeviceToHost, m->stream));
-        if (var) GEM_CUDA(m, cudaMemcpyAsync(var + off, m->sc.hv, b, cudaMemcpyDeviceToHost, m->stream));
-        if (z_ts) GEM_CUDA(m, cudaMemcpyAsync(z_ts + off, m->sc.h, b, cudaMemcpyDeviceToHost, m->stream));
-        if (x_ts) GEM_CUDA(m, cudaMemcpyAsync(x_ts + off, m->d_xt, b, cudaMemcpyDeviceToHost, m->stream));
-        if (y_ts) GEM_CUDA(m, cudaMemcpyAsync(y_ts + off, m->d_yt, b, cudaMemcpyDeviceToHost, m->stream));
-        if ((rc = read_counters(m, cn, true))) return rc;
+        in.key_out = m->d_keyout; in.h_out = m->d_h; in.hv_out = m->d_hv; in.xt_out = m->d_xt; in.yt_out = m->d_yt;
+        const FoldSrc fs{SRC_SOA, nullptr};
+        if ((rc = enqueue_add<SRC_SOA>(m, in, fs, cn, fp, nullptr, nullptr, false, false, true))) break; // lowest-scan only
+        if (map_index && e == cudaSuccess) e = cudaMemcpyAsync(map_index + off, m->d_keyout, b, cudaMemcpyDeviceToHost, m->stream);
+        if (var && e == cudaSuccess) e = cudaMemcpyAsync(var + off, m->d_hv, b, cudaMemcpyDeviceToHost, m->stream);
+        if (z_ts && e == cudaSuccess) e = cudaMemcpyAsync(z_ts + off, m->d_h, b, cudaMemcpyDeviceToHost, m->stream);
+        if (x_ts && e == cudaSuccess) e = cudaMemcpyAsync(x_ts + off, m->d_xt, b, cudaMemcpyDeviceToHost, m->stream);
+        if (y_ts && e == cudaSuccess) e = cudaMemcpyAsync(y_ts + off, m->d_yt, b, cudaMemcpyDeviceToHost, m->stream);
+        if (e != cudaSuccess) { rc = fail(m, GEM_ERR_CUDA, cudaGetErrorString(e)); break; }
+        rc = read_counters(m, cn, true);
     }
-    return GEM_OK;
+    m->pending.insert(m->pending.begin(), keep.begin(), keep.end());
+    return rc;
 }
 
 int gem_fuse(gem_map *m, int n, const int *index, const int *R, const int *G, const int *B, const float *intensity,
              const float *height, const float *var)
 {
     if (!m || n < 0 || (n > 0 && (!index || !height || !var))) return fail(m, GEM_ERR_INVALID, "gem_fuse: bad argument");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = ensure_compat_staging(m);
     if (rc) return rc;
     memset(&m->stats, 0, sizeof m->stats);
     if (n == 0) { if ((rc = flush_all_pending(m))) return rc; return gem_sync(m); }
+    if ((rc = drain(m))) return rc;
     for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
         const size_t b = (size_t)cn * 4;
         GEM_CUDA(m, cudaMemcpyAsync(m->d_keyin, index + off, b, cudaMemcpyHostToDevice, m->stream));
-        GEM_CUDA(m, cudaMemcpyAsync(m->sc.h, height + off, b, cudaMemcpyHostToDevice, m->stream));
-        GEM_CUDA(m, cudaMemcpyAsync(m->sc.hv, var + off, b, cudaMemcpyHostToDevice, m->stream));
-        AttrInput a{};
-        if (R) { GEM_CUDA(m, cudaMemcpyAsync(m->d_R, R + off, b, cudaMemcpyHostToDevice, m->stream)); a.R = m->d_R; }
-        if (G) { GEM_CUDA(m, cudaMemcpyAsync(m->d_G, G + off, b, cudaMemcpyHostToDevice, m->stream)); a.G = m->d_G; }
-        if (B) { GEM_CUDA(m, cudaMemcpyAsync(m->d_B, B + off, b, cudaMemcpyHostToDevice, m->stream)); a.B = m->d_B; }
+        GEM_CUDA(m, cudaMemcpyAsync(m->d_h, height + off, b, cudaMemcpyHostToDevice, m->stream));
+        GEM_CUDA(m, cudaMemcpyAsync(m->d_hv, var + off, b, cudaMemcpyHostToDevice, m->stream));
+        BinSource in{};
+        in.key_in = m->d_keyin; in.h_in = m->d_h; in.hv_in = m->d_hv; in.ncells = (int)m->nc;
+        if (R) { GEM_CUDA(m, cudaMemcpyAsync(m->d_R, R + off, b, cudaMemcpyHostToDevice, m->stream)); in.R = m->d_R; }
+        if (G) { GEM_CUDA(m, cudaMemcpyAsync(m->d_G, G + off, b, cudaMemcpyHostToDevice, m->stream)); in.G = m->d_G; }
+        if (B) { GEM_CUDA(m, cudaMemcpyAsync(m->d_B, B + off, b, cudaMemcpyHostToDevice, m->stream)); in.B = m->d_B; }
         if (intensity) {
             GEM_CUDA(m, cudaMemcpyAsync(m->d_int, intensity + off, b, cudaMemcpyHostToDevice, m->stream));
-            a.intensity = m->d_int;
+            in.inten_in = m->d_int;
         }
-        RegionOps ro;
-        int rb = 0;
-        if ((rc = take_region_ops(m, ro, rb))) return rc;
-        const Scratch sc = cur_scratch(m);
-        const int pb = blocks_for((size_t)cn, ADD_BLOCK, 148 * 16);
-        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_count_keys<<<pb + rb, ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, m->d_keyin, cn, (int)m->nc, sc, ro, pb));
-        if ((rc = run_group_fold<ATTR_INT_ARRAYS>(m, sc, a, cn, true, false))) return rc;
+        const FoldSrc fs{SRC_KEYS, in.inten_in};
+        const FrameParams none{};
+        if ((rc = enqueue_add<SRC_KEYS>(m, in, fs, cn, none, nullptr, nullptr, false, true, false))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc;
     }
     return GEM_OK;
@@ -1045,6 +1067,7 @@ int gem_fuse(gem_map *m, int n, const int *index, const int *R, const int *G, co
 int gem_var_update(gem_map *m, float dv)
 {
     if (!m) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     // x + 0.0f == x for every non-NaN x: the GEM node always passes 0 (ElevationMapping.cpp:944-945)
     if (dv == 0.0f) return GEM_OK;
@@ -1059,6 +1082,7 @@ int gem_compute_features(gem_map *m)
 {
     if (!m) return GEM_ERR_INVALID;
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_compute_features: tiled handles take the halo-padded tile: use gem_compute_features_tiled");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     { int rcf = flush_for_observer(m); if (rcf) return rcf; }
     GEM_LAUNCH(m, GEM_PROF_FEATURES, k_features<false><<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, nullptr));
@@ -1080,6 +1104,7 @@ int gem_map_feature(gem_map *m, float *elevation, float *var, int *R, int *G, in
                     float *traver, float *intensity)
 {
     if (!m) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
     int rc = gem_compute_features(m);
     if (rc) return rc;
     SetDev sd(m->dev);
@@ -1095,6 +1120,7 @@ int gem_map_feature(gem_map *m, float *elevation, float *var, int *R, int *G, in
 int gem_get_layer_device(gem_map *m, int layer, void *out_device)
 {
     if (!m || !out_device || layer < 0 || layer > 10) return fail(m, GEM_ERR_INVALID, "gem_get_layer_device: bad argument");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     { int rcf = flush_for_observer(m); if (rcf) return rcf; }
     GEM_LAUNCH(m, GEM_PROF_OTHER, k_unpack_layer<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml, m->nc, layer, out_device));
@@ -1106,6 +1132,7 @@ int gem_compute_features_tiled(gem_map *m, const float *padded_elevation)
 {
     if (!m || !padded_elevation) return fail(m, GEM_ERR_INVALID, "gem_compute_features_tiled: bad argument");
     if (!m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_compute_features_tiled: handle is not tiled");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     { int rcf = flush_for_observer(m); if (rcf) return rcf; }
     GEM_LAUNCH(m, GEM_PROF_FEATURES, k_features<true><<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, padded_elevation));
@@ -1117,17 +1144,18 @@ int gem_raytracing_tiled(gem_map *m, const float *global_lowest)
 {
     if (!m || !global_lowest) return fail(m, GEM_ERR_INVALID, "gem_raytracing_tiled: bad argument");
     if (!m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_raytracing_tiled: handle is not tiled");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     { int rcf = flush_for_observer(m); if (rcf) return rcf; }
     const size_t ng = (size_t)m->L * m->L;
-    if (!m->d_gbitmap) { int rc = dev_alloc(m, &m->d_gbitmap, ng / 32 + 1); if (rc) return rc; }
-    int *ray_count = &m->ctr_buf[m->ctr_cur ^ 1]->pad4[0];
+    { int rc = ensure_ray_scratch(m, ng); if (rc) return rc; }
+    int *ray_count = m->d_raylist + m->nc;
     GEM_CUDA(m, cudaMemsetAsync(ray_count, 0, sizeof(int), m->stream));
     MapLayers mlg = m->ml;
     mlg.lowest = const_cast<float *>(global_lowest); // rays probe the replicated, map-wide lowest layer
-    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_collect<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, m->cfg.obstacle_threshold, m->sc.cellBase, ray_count));
-    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_lowest_bitmap<<<blocks_for(ng, 256, 1 << 30), 256, 0, m->stream>>>(global_lowest, (int)ng, m->d_gbitmap));
-    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_trace<<<148 * 8, 256, 0, m->stream>>>(m->geom, mlg, m->d_gbitmap, m->sensorZ, m->sc.cellBase, ray_count));
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_collect<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, m->cfg.obstacle_threshold, m->d_raylist, ray_count));
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_lowest_bitmap<<<blocks_for(ng, 256, 1 << 30), 256, 0, m->stream>>>(global_lowest, (int)ng, m->d_bitmap));
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_trace<<<148 * 8, 256, 0, m->stream>>>(m->geom, mlg, m->d_bitmap, m->sensorZ, m->d_raylist, ray_count));
     GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml.lowest, m->nc, 10.0f)); // own tile's lowest
     GEM_CUDA(m, cudaGetLastError());
     GEM_CUDA(m, cudaStreamSynchronize(m->stream));
@@ -1138,15 +1166,16 @@ int gem_raytracing(gem_map *m)
 {
     if (!m) return GEM_ERR_INVALID;
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_raytracing: tiled handles take the map-wide lowest layer: use gem_raytracing_tiled");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     { int rcf = flush_for_observer(m); if (rcf) return rcf; }
-    // ray list lives in cellBase (free between add calls), its length in the spare counter buffer
-    int *ray_count = &m->ctr_buf[m->ctr_cur ^ 1]->pad4[0];
+    { int rc = ensure_ray_scratch(m, m->nc); if (rc) return rc; }
+    int *ray_count = m->d_raylist + m->nc; // the list's length lives behind it
     GEM_CUDA(m, cudaMemsetAsync(ray_count, 0, sizeof(int), m->stream));
-    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_collect<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, m->cfg.obstacle_threshold, m->sc.cellBase, ray_count));
-    uint32_t *bitmap = (uint32_t *)m->sc.rank; // nc/32 words <= max_points (checked at create)
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_collect<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, m->cfg.obstacle_threshold, m->d_raylist, ray_count));
+    uint32_t *bitmap = m->d_bitmap;
     GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_lowest_bitmap<<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->ml.lowest, (int)m->nc, bitmap));
-    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_trace<<<148 * 8, 256, 0, m->stream>>>(m->geom, m->ml, bitmap, m->sensorZ, m->sc.cellBase, ray_count));
+    GEM_LAUNCH(m, GEM_PROF_RAYTRACE, k_ray_trace<<<148 * 8, 256, 0, m->stream>>>(m->geom, m->ml, bitmap, m->sensorZ, m->d_raylist, ray_count));
     GEM_LAUNCH(m, GEM_PROF_CLEAR, k_fill<<<blocks_for(m->nc, 256), 256, 0, m->stream>>>(m->ml.lowest, m->nc, 10.0f)); // G_Clear_maplowest
     GEM_CUDA(m, cudaGetLastError());
     GEM_CUDA(m, cudaStreamSynchronize(m->stream)); // gpu.cu:1312
@@ -1156,6 +1185,7 @@ int gem_raytracing(gem_map *m)
 int gem_opt_move(gem_map *m, const float opt_p[2], float height_update, float aligned_out[2])
 {
     if (!m || !opt_p) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     float c[2] = {m->geom.cx, m->geom.cy};
     for (int i = 0; i < 2; i++) { // alignedPosition gpu.cu:1203-1213
@@ -1174,6 +1204,7 @@ int gem_opt_move(gem_map *m, const float opt_p[2], float height_update, float al
 int gem_closeloop(gem_map *m, const float up[2], float height_update)
 {
     if (!m || !up) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     float c[2] = {m->geom.cx, m->geom.cy};
     for (int i = 0; i < 2; i++) { // gpu.cu:1242-1247
@@ -1194,6 +1225,7 @@ int gem_colourise_points(gem_map *m, void *xyzi, int n, const double Tc[12], con
 {
     if (!m || n < 0 || (n > 0 && (!xyzi || !rgba_out)) || !Tc || !Tl || !bgr || width < 1 || height < 1 || row_stride < 3 * width)
         return fail(m, GEM_ERR_INVALID, "gem_colourise_points: bad argument");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     ProjParams pp;
     for (int i = 0; i < 3; i++) // P_lidar2img = Tcamera * TLidar (ElevationMapping.cpp:347), double, left-to-right sums
@@ -1213,6 +1245,7 @@ int gem_export_layers(gem_map *m, float *host_layers[9])
 {
     if (!m || !host_layers) return GEM_ERR_INVALID;
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_export_layers: not available on tiled handles");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = ensure_out_staging(m);
     if (rc) return rc;
@@ -1231,6 +1264,7 @@ int gem_export_orthomosaic(gem_map *m, unsigned char *host_bgr)
 {
     if (!m || !host_bgr) return fail(m, GEM_ERR_INVALID, "gem_export_orthomosaic: null argument");
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_export_orthomosaic: not available on tiled handles");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = ensure_out_staging(m);
     if (rc) return rc;
@@ -1248,6 +1282,7 @@ int gem_export_visual_points(gem_map *m, float *host_xyz, unsigned char *host_rg
     if (!m || !count_out || capacity < 0 || (capacity > 0 && (!host_xyz || !host_rgb)))
         return fail(m, GEM_ERR_INVALID, "gem_export_visual_points: bad argument");
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_export_visual_points: not available on tiled handles");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = ensure_out_staging(m);
     if (rc) return rc;
@@ -1275,6 +1310,7 @@ int gem_snapshot_shown(gem_map *m)
 {
     if (!m) return GEM_ERR_INVALID;
     if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_snapshot_shown: not available on tiled handles");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc;
     if ((rc = flush_for_observer(m))) return rc;
@@ -1294,6 +1330,7 @@ int gem_harvest_scrolled_out(gem_map *m, const float current_xy[2], const float 
     if (!m || !current_xy || !shift_xy || !count_out || capacity < 0 || (capacity > 0 && !host_points32))
         return fail(m, GEM_ERR_INVALID, "gem_harvest_scrolled_out: bad argument");
     if (!m->prev_valid) return fail(m, GEM_ERR_INVALID, "gem_harvest_scrolled_out: no snapshot (call gem_snapshot_shown first)");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = ensure_out_staging(m);
     if (rc) return rc;
@@ -1321,6 +1358,7 @@ int gem_harvest_scrolled_out(gem_map *m, const float current_xy[2], const float 
 int gem_get_layer(gem_map *m, int layer, void *host_out)
 {
     if (!m || !host_out || layer < 0 || layer > 9) return fail(m, GEM_ERR_INVALID, "gem_get_layer: bad argument");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = ensure_out_staging(m);
     if (rc) return rc;
@@ -1332,6 +1370,7 @@ int gem_get_layer(gem_map *m, int layer, void *host_out)
 int gem_set_layer(gem_map *m, int layer, const void *host_in)
 {
     if (!m || !host_in || layer < 0 || layer > 9) return fail(m, GEM_ERR_INVALID, "gem_set_layer: bad argument");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = ensure_out_staging(m);
     if (rc) return rc;
@@ -1347,6 +1386,7 @@ int gem_set_layer(gem_map *m, int layer, const void *host_in)
 int gem_get_state(gem_map *m, float centre[2], int start[2], float *sensor_z)
 {
     if (!m) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
     if (centre) { centre[0] = m->geom.cx; centre[1] = m->geom.cy; }
     if (start) { start[0] = m->geom.sx; start[1] = m->geom.sy; }
     if (sensor_z) *sensor_z = m->sensorZ;
@@ -1356,6 +1396,7 @@ int gem_get_state(gem_map *m, float centre[2], int start[2], float *sensor_z)
 int gem_get_stats(gem_map *m, gem_stats *out)
 {
     if (!m || !out) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     if (m->stats.points_in > 0 && m->stats.cells_touched == 0 && m->stats.points_binned == 0) {
         // device-pointer call: counters not fetched yet
@@ -1371,6 +1412,8 @@ int gem_get_stats(gem_map *m, gem_stats *out)
 int gem_profile_enable(gem_map *m, int on)
 {
     if (!m) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
+    if (on && !m->profiling) { int rc = drain(m); if (rc) return rc; }
     m->profiling = on != 0;
     return GEM_OK;
 }
@@ -1378,7 +1421,10 @@ int gem_profile_enable(gem_map *m, int on)
 int gem_profile_read(gem_map *m, gem_profile *out, int reset)
 {
     if (!m || !out) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
     SetDev sd(m->dev);
+    { int rc = drain(m); if (rc) return rc; }
+    if (m->front_stream) GEM_CUDA(m, cudaStreamSynchronize(m->front_stream));
     GEM_CUDA(m, cudaStreamSynchronize(m->stream));
     for (auto &sp : m->spans) {
         float ms = 0.0f;
@@ -1406,6 +1452,7 @@ int gem_selftest_division(gem_map *m, unsigned long long seed, unsigned long lon
                           unsigned long long *fast_out)
 {
     if (!m || !mismatches_out) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     unsigned long long *d = nullptr;
     GEM_CUDA(m, cudaMalloc((void **)&d, 16));
@@ -1435,14 +1482,18 @@ int gem_route_points(gem_map *m, const void *xyzi, const void *rgba, int n, cons
         return fail(m, GEM_ERR_INVALID, "gem_route_points: bad argument");
     if (n > m->P) return fail(m, GEM_ERR_INVALID, "gem_route_points: n exceeds max_points");
     if (tiles_r * tiles_c > ROUTE_MAX_OWNERS) return fail(m, GEM_ERR_INVALID, "gem_route_points: too many tiles");
+    if (bucket_stride > 0 && bucket_stride < n) // one owner may receive all n records
+        return fail(m, GEM_ERR_INVALID, "gem_route_points: bucket_stride must be 0 (packed) or >= n");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     const FrameParams fp = make_frame(frame);
     MapGeom gg = m->geom;
     gg.tiled = 0; // routing works on global geographic indices
     if (bucket_stride > 0) // padded layout: unused slots must read as "no record" (gkey = -1)
         GEM_CUDA(m, cudaMemsetAsync(rec_out, 0xff, (size_t)tiles_r * tiles_c * bucket_stride * sizeof(RouteRec), m->stream));
+    { int rc = ensure_route_scratch(m); if (rc) return rc; }
     const cudaError_t e = route_points(m->stream, gg, fp, (const float4 *)xyzi, (const uchar4 *)rgba, n, tiles_r,
-                                       tiles_c, cur_scratch(m), m->nc, (RouteRec *)rec_out, counts_out, bucket_stride);
+                                       tiles_c, m->route_sc, (RouteRec *)rec_out, counts_out, bucket_stride);
     m->launches += 3;
     if (e != cudaSuccess) return fail(m, GEM_ERR_CUDA, std::string("gem_route_points: ") + cudaGetErrorString(e));
     return GEM_OK;
@@ -1468,6 +1519,7 @@ int gem_route_points_peer(gem_map *m, const void *xyzi, const void *rgba, int n,
         return fail(m, GEM_ERR_INVALID, "gem_route_points_peer: bad argument (bucket_stride must be >= n)");
     if (n > m->P) return fail(m, GEM_ERR_INVALID, "gem_route_points_peer: n exceeds max_points");
     if (no > ROUTE_MAX_OWNERS) return fail(m, GEM_ERR_INVALID, "gem_route_points_peer: too many tiles");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
     int rc = GEM_OK;
     if (!m->d_owner_cnt && (rc = dev_alloc(m, &m->d_owner_cnt, ROUTE_MAX_OWNERS))) return rc;
@@ -1477,8 +1529,9 @@ int gem_route_points_peer(gem_map *m, const void *xyzi, const void *rgba, int n,
     PeerTable pt;
     memset(&pt, 0, sizeof pt);
     for (int o = 0; o < no; o++) { pt.recv[o] = peer_recv[o]; pt.counts[o] = peer_counts[o]; }
+    if ((rc = ensure_route_scratch(m))) return rc;
     const cudaError_t e = route_points(m->stream, gg, fp, (const float4 *)xyzi, (const uchar4 *)rgba, n, tiles_r, tiles_c,
-                                       cur_scratch(m), m->nc, nullptr, m->d_owner_cnt, bucket_stride, &pt, my_rank);
+                                       m->route_sc, nullptr, m->d_owner_cnt, bucket_stride, &pt, my_rank);
     m->launches += 3;
     if (e != cudaSuccess) return fail(m, GEM_ERR_CUDA, std::string("gem_route_points_peer: ") + cudaGetErrorString(e));
     return GEM_OK;
@@ -1487,19 +1540,20 @@ int gem_route_points_peer(gem_map *m, const void *xyzi, const void *rgba, int n,
 static int fuse_records_impl(gem_map *m, const void *rec, int n, const int *src_counts, int stride)
 {
     if (!m || n < 0 || (n > 0 && !rec)) return fail(m, GEM_ERR_INVALID, "gem_fuse_records: bad argument");
+    Lock lk(m->mu);
     SetDev sd(m->dev);
-    int rc = flush_all_pending(m);
-    if (rc) return rc;
+    int rc = GEM_OK;
     memset(&m->stats, 0, sizeof m->stats);
+    if (n == 0) return flush_all_pending(m);
     for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
-        const Scratch sc = cur_scratch(m);
-        GEM_LAUNCH(m, GEM_PROF_TRANSFORM_BIN, k_count_records<<<blocks_for((size_t)cn, ADD_BLOCK, 1 << 30), ADD_BLOCK, 0, m->stream>>>(m->geom, (const RouteRec *)rec + off, cn, sc, src_counts, stride));
-        GEM_LAUNCH(m, GEM_PROF_ALLOC, k_alloc_cells<<<blocks_for((size_t)cn, ADD_BLOCK, 148 * 4), ADD_BLOCK, 0, m->stream>>>(sc));
-        GEM_LAUNCH(m, GEM_PROF_SCATTER, k_scatter_records<<<blocks_for((size_t)cn, ADD_BLOCK, 1 << 30), ADD_BLOCK, 0, m->stream>>>((const RouteRec *)rec + off, cn, sc));
-        GEM_LAUNCH(m, GEM_PROF_FOLD, k_fold<<<blocks_for((size_t)cn, ADD_BLOCK, 148 * 8), ADD_BLOCK, 0, m->stream>>>(m->geom, m->ml, sc, 1, 1));
-        GEM_CUDA(m, cudaGetLastError());
-        call_done(m);
+        BinSource in{};
+        in.rec = (const RouteRec *)rec + off;
+        in.src_counts = src_counts; // counted buffers are never chunked (n <= max_points is checked by the caller)
+        in.stride = stride;
+        const FoldSrc fs{SRC_RECORDS, in.rec};
+        const FrameParams none{};
+        if ((rc = enqueue_add<SRC_RECORDS>(m, in, fs, cn, none, nullptr, nullptr, false, true, true))) return rc;
         if (n > m->P && (rc = read_counters(m, cn, true))) return rc;
     }
     if (n <= m->P) m->stats.points_in = n;

@@ -7,19 +7,12 @@
 // order) reproduces the global point order, so the tiled result is bit-identical to the
 // single-GPU result on the concatenated cloud.
 #pragma once
-#include "gem_kernels.cuh"
+#include "gem_add.cuh"
 
 namespace gem {
 
 constexpr int ROUTE_MAX_OWNERS = 64;
 constexpr int ROUTE_BLOCK = 256;
-
-struct RouteRec { // 20 bytes on the wire
-    int gkey;     // global geographic linear index gx*L+gy
-    float h, var;
-    uint32_t rgb;
-    float intensity;
-};
 
 // pass 1: transform, owner id, per-block owner histogram
 __global__ void __launch_bounds__(ROUTE_BLOCK)
@@ -167,80 +160,31 @@ k_route_write_peer(const float4 *xyzi, const uchar4 *rgba, int n, int n_owners, 
     }
 }
 
-// scratch layout for routing reuses the per-point arrays of the handle:
-//   key -> owner, rank -> gkey, h/hv as usual; blockCounts lives in cellBase.
+// per-point scratch of the routing passes
+struct RouteScratch {
+    int *owner, *gkey;
+    float *h, *hv;
+    int *blockCounts; // [owners][blocks]
+    size_t blockCounts_capacity;
+};
 inline cudaError_t route_points(cudaStream_t st, const MapGeom &g, const FrameParams &fp, const float4 *xyzi,
-                                const uchar4 *rgba, int n, int tiles_r, int tiles_c, const Scratch &sc,
-                                size_t cellBase_capacity, RouteRec *out, int *counts_out, int bucket_stride,
+                                const uchar4 *rgba, int n, int tiles_r, int tiles_c, const RouteScratch &sc,
+                                RouteRec *out, int *counts_out, int bucket_stride,
                                 const PeerTable *peer = nullptr, int my_rank = 0)
 {
     const int n_owners = tiles_r * tiles_c;
     const int nblocks = n > 0 ? (n + ROUTE_BLOCK - 1) / ROUTE_BLOCK : 1;
-    if ((size_t)n_owners * nblocks > cellBase_capacity) return cudaErrorInvalidValue;
+    if ((size_t)n_owners * nblocks > sc.blockCounts_capacity) return cudaErrorInvalidValue;
     const int tile_h = (g.L + tiles_r - 1) / tiles_r, tile_w = (g.L + tiles_c - 1) / tiles_c;
-    k_route_count<<<nblocks, ROUTE_BLOCK, 0, st>>>(g, fp, xyzi, n, tile_h, tile_w, tiles_c, n_owners, sc.key, sc.rank,
-                                                  sc.h, sc.hv, sc.cellBase);
-    k_route_scan<<<1, 1024, 0, st>>>(sc.cellBase, n_owners, nblocks, counts_out);
+    k_route_count<<<nblocks, ROUTE_BLOCK, 0, st>>>(g, fp, xyzi, n, tile_h, tile_w, tiles_c, n_owners, sc.owner, sc.gkey,
+                                                  sc.h, sc.hv, sc.blockCounts);
+    k_route_scan<<<1, 1024, 0, st>>>(sc.blockCounts, n_owners, nblocks, counts_out);
     if (peer)
-        k_route_write_peer<<<nblocks, ROUTE_BLOCK, 0, st>>>(xyzi, rgba, n, n_owners, sc.key, sc.rank, sc.h, sc.hv, sc.cellBase,
+        k_route_write_peer<<<nblocks, ROUTE_BLOCK, 0, st>>>(xyzi, rgba, n, n_owners, sc.owner, sc.gkey, sc.h, sc.hv, sc.blockCounts,
                                                           counts_out, *peer, my_rank, bucket_stride);
     else
-        k_route_write<<<nblocks, ROUTE_BLOCK, 0, st>>>(xyzi, rgba, n, n_owners, sc.key, sc.rank, sc.h, sc.hv, sc.cellBase, out, bucket_stride);
+        k_route_write<<<nblocks, ROUTE_BLOCK, 0, st>>>(xyzi, rgba, n, n_owners, sc.owner, sc.gkey, sc.h, sc.hv, sc.blockCounts, out, bucket_stride);
     return cudaGetLastError();
-}
-
-// count/scatter for received records (fold happens in k_fold)
-// src_counts != nullptr: the buffer holds buckets of `stride` slots, bucket s filled up to src_counts[s]
-__device__ __forceinline__ bool record_slot_valid(int i, const int *src_counts, int stride)
-{
-    if (!src_counts) return true;
-    const int s = i / stride;
-    return (i - s * stride) < src_counts[s];
-}
-
-__global__ void __launch_bounds__(256) k_count_records(MapGeom g, const RouteRec *rec, int n, Scratch sc, const int *src_counts, int stride)
-{
-    pdl_launch_dependents();
-    pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
-    zero_next_counters(sc, i);
-    int key = -1;
-    bool first = false;
-    if (i < n) {
-        const int gkey = record_slot_valid(i, src_counts, stride) ? rec[i].gkey : -1;
-        if (gkey >= 0) {
-            const int gx = gkey / g.L, gy = gkey - gx * g.L;
-            key = local_key(g, gx, gy);
-        }
-        sc.key[i] = key;
-        if (key >= 0) {
-            const int rk = atomicAdd(&sc.cnt[key], 1);
-            sc.rank[i] = rk;
-            first = (rk == 0);
-        }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, first);
-    if (m) {
-        int base = 0;
-        const int leader = __ffs(m) - 1;
-        if ((int)lane == leader) base = atomicAdd(&sc.ctr->ntouched, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (first) sc.touched[base + __popc(m & ((1u << lane) - 1u))] = key;
-    }
-}
-__global__ void __launch_bounds__(256) k_scatter_records(const RouteRec *rec, int n, Scratch sc)
-{
-    pdl_launch_dependents();
-    pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int key = sc.key[i];
-    if (key < 0) return;
-    const int pos = sc.cellBase[key] + sc.rank[i];
-    const RouteRec r = rec[i];
-    sc.recA[pos] = make_uint4((uint32_t)i, __float_as_uint(r.h), __float_as_uint(r.var), with_colour_flag(r.rgb, r.intensity));
-    sc.recI[pos] = r.intensity;
 }
 
 } // namespace gem

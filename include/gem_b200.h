@@ -18,8 +18,11 @@
  *     pointers are asynchronous on that stream, functions taking host pointers return
  *     after the result is visible to the host (like the reference wrappers, which are all
  *     host-synchronous);
- *   - a handle is thread-compatible: calls on the same handle must be serialised by the
- *     caller (the reference node does so with MapMutex_, ElevationMapping.cpp:277,292);
+ *   - a handle is thread-safe: every entry point takes the handle's (recursive) mutex, so the
+ *     reference node's three threads (processpoints: Process_points OUTSIDE MapMutex_ and Fuse
+ *     inside, ElevationMapping.cpp:271-282; processmapcells :286-300; the spinner's Move /
+ *     Map_feature / Raytracing :388-421) may enter concurrently; calls are serialised, and
+ *     what one call enqueued is ordered before the next on the handle's stream;
  *   - there is NO CPU fallback: gem_create fails with GEM_ERR_NO_DEVICE without a GPU.
  *
  * Layer layout seen through this ABI is the reference's: row-major L*L arrays, index
@@ -122,9 +125,10 @@ int gem_destroy(gem_map *m);
 int gem_sync(gem_map *m); /* wait for the handle's stream */
 /* the cudaStream_t all work of this handle is ordered on (record your own events there) */
 void *gem_get_stream(gem_map *m);
-/* debug: per-phase %globaltimer stamps (ns) of the last fused add launch (9 phase stamps of block 0,
- * [9] = end of the last block, [10] = last block past the third barrier) */
-int gem_debug_phase_stamps(gem_map *m, int enable, unsigned long long out[16]);
+/* enqueue everything the pipelined add calls have deferred (the fold of the last gem_add_points_stream /
+ * _multi / _host_async call) on the handle's stream without waiting for it; gem_sync and every call that
+ * reads or changes the map do this implicitly */
+int gem_flush(gem_map *m);
 
 /* Move (gpu.cu:1004-1083): scroll the circular buffer to follow pos[0..1], record
  * pos[2] as sensorZatLowestScan.  Outputs may be NULL. */
@@ -133,18 +137,24 @@ int gem_move(gem_map *m, const float pos[3], float centre_out[2], int start_out[
 
 /* ---- fused hot path: Process_points + Fuse with device-resident intermediates --------
  * xyzi: n x float4 {x, y, z, intensity} in the sensor frame; rgba: n x uchar4 {r,g,b,-}
- * or NULL (colour path off).  Equivalent to SensorProcessorBase::process +
+ * or NULL (colour path off).  NOTE (reference behaviour, gpu.cu:488): a cell takes a point's
+ * intensity AND colour only when R, G, B and intensity are ALL non-zero, so with rgba == NULL
+ * (or for points whose colour has a zero channel) the intensity layer is not written either --
+ * LiDAR-only clouds that want the intensity layer must pass a non-zero dummy colour.  Equivalent to SensorProcessorBase::process +
  * ElevationMapping::processpoints (ElevationMapping.cpp:254-283). */
 int gem_add_points(gem_map *m, const void *xyzi_device, const void *rgba_device, int n,
                    const gem_frame *frame);
 int gem_add_points_host(gem_map *m, const void *xyzi_host, const void *rgba_host, int n,
                         const gem_frame *frame);
-/* Stream mode: same result as gem_add_points, but consecutive calls are software-pipelined: the
- * transform/bin, allocation and scatter kernels of frame i+1 run on a second stream while the
- * per-cell fold of frame i (the only kernel that touches the layers, and mostly a serial tail)
- * is still running; scratch is double-buffered.  Contract: the device inputs must already be
- * complete when the call is made (they are read on an internal stream, not on gem_get_stream)
- * and must stay valid until the next-but-one call or gem_sync.  n <= max_points. */
+/* Stream mode: same result as gem_add_points, but consecutive calls are software-pipelined: call
+ * i+1 issues ONE two-node CUDA graph {fold of frame i || bin of frame i+1} on the handle's
+ * stream (the fold is mostly a serial tail, the bin kernel is throughput work; per-cell scratch
+ * is double-buffered inside the 32-byte cell record).  The fold of the last frame is issued by
+ * the next call of any kind that reads or changes the map, by gem_flush or by gem_sync.
+ * Contract: the device inputs are read by the bin kernel of this call AND (intensities) by the
+ * deferred fold: they must stay valid until two further stream calls have COMPLETED on the
+ * stream, or until gem_sync.  n <= max_points.  GEM_B200_PIPE=stream selects two streams +
+ * events instead of the graph, GEM_B200_PIPE=off makes this call identical to gem_add_points. */
 int gem_add_points_stream(gem_map *m, const void *xyzi_device, const void *rgba_device, int n,
                           const gem_frame *frame);
 /* Several clouds in one launch (multi-sensor rigs, BASELINE config 5): the device buffers hold
@@ -155,9 +165,10 @@ int gem_add_points_stream(gem_map *m, const void *xyzi_device, const void *rgba_
 int gem_add_points_multi(gem_map *m, const void *xyzi_device, const void *rgba_device, int n_segments,
                          const int *offsets, const gem_frame *frames);
 /* Pipelined host ingest: like gem_add_points_host but returns without waiting.  The copy runs on
- * a second stream into one of two staging buffers, so frame i+1's H2D overlaps frame i's kernels;
- * the per-call counters are read back asynchronously (gem_get_stats after gem_sync).  The host
- * buffers must be pinned (gem_host_alloc / cudaHostRegister) and stay untouched until the call
+ * a second stream into one of three staging buffers, so frame i+1's H2D overlaps frame i's kernels
+ * (which run pipelined like gem_add_points_stream); every call also reads back the counters of the
+ * newest frame whose fold has been issued (gem_get_stats gives the last frame's after a drain).  The
+ * host buffers must be pinned (gem_host_alloc / cudaHostRegister) and stay untouched until the call
  * after next on this handle, or gem_sync().  n must not exceed max_points. */
 int gem_add_points_host_async(gem_map *m, const void *xyzi_pinned, const void *rgba_pinned, int n,
                               const gem_frame *frame);
@@ -240,11 +251,15 @@ int gem_get_stats(gem_map *m, gem_stats *out);
 /* ---- launch accounting and per-kernel device timing ------------------------------------
  * The library counts every kernel it launches.  With profiling enabled each launch is also
  * bracketed by CUDA events on the handle's stream (costs ~2 us per launch: use a separate
- * pass, not the timed one).  gem_profile_read synchronises the stream. */
+ * pass, not the timed one) and the pipelined add calls fall back to the serial schedule
+ * (bin, then fold, nothing overlapped), so the per-kernel durations are uncontended.
+ * gem_profile_read synchronises the stream. */
 enum {
-    GEM_PROF_TRANSFORM_BIN = 0, GEM_PROF_ALLOC = 1, GEM_PROF_SCATTER = 2, GEM_PROF_FOLD = 3,
+    GEM_PROF_TRANSFORM_BIN = 0, /* k_bin: transform + bin + in-kernel slot allocation + record store */
+    GEM_PROF_ALLOC = 1, GEM_PROF_SCATTER = 2, /* unused since the round-2 add path (kept for ABI stability) */
+    GEM_PROF_FOLD = 3,
     GEM_PROF_CLEAR = 4, GEM_PROF_FEATURES = 5, GEM_PROF_RAYTRACE = 6, GEM_PROF_OTHER = 7,
-    GEM_PROF_FUSED = 8, /* k_add_fused: all four add phases in one cooperative launch */
+    GEM_PROF_ROUTE = 8, /* tiled maps: the routing kernel */
     GEM_PROF_CLASSES = 9
 };
 typedef struct gem_profile {
