@@ -71,6 +71,7 @@ SYMBOLS = {
     "gem_sync": (C.c_int, [_P]),
     "gem_get_stream": (C.c_void_p, [_P]),
     "gem_flush": (C.c_int, [_P]),
+    "gem_debug_stamps": (C.c_int, [_P, C.c_int, C.POINTER(C.c_ulonglong)]),
     "gem_move": (C.c_int, [_P, _FP, _FP, _IP, _FP]),
     "gem_add_points": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),
     "gem_add_points_host": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),

@@ -43,10 +43,10 @@ struct PendingFold {
     int n = 0;
 };
 
-struct FrameGraph { // {fold of the previous call || bin of this call} as one two-node CUDA graph
+struct FrameGraph { // {long lists || the other lists of the previous call || bin of this call} as one three-node CUDA graph
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t fold_node = nullptr, bin_node = nullptr;
+    cudaGraphNode_t long_node = nullptr, fold_node = nullptr, bin_node = nullptr;
 };
 
 struct gem_map {
@@ -68,6 +68,10 @@ struct gem_map {
     unsigned call_no = 0;
     BinCounters *ctr_last = nullptr; // counters of the last add call
     PendingFold pend;
+    // tuning, measured on B200 with scripts/pipe_sweep.sh (profiles/r2_pipe_sweep.txt): GEM_B200_FOLD_BLOCKS, GEM_B200_LONG_BLOCKS,
+    // GEM_B200_EXCLUSIVE=1 pads the kernels' shared memory so that k_fold_long's blocks get SMs of their own
+    int fold_max_blocks = 148 * 2, long_blocks = LONG_BLOCKS;
+    size_t bin_smem = 0, fold_smem = FOLD_SMEM_USED, long_smem = (LONG_BLOCK / 32) * sizeof(LongScratch);
     int pipe_mode = 2;               // 0: never defer the fold; 1: two streams + events; 2: CUDA graph per call
     std::map<const void *, FrameGraph> graphs; // keyed by the bin kernel function
     cudaStream_t front_stream = nullptr;      // pipe_mode 1: the bin kernels run here
@@ -89,6 +93,7 @@ struct gem_map {
     MapGeom prev_geom{};
     bool prev_valid = false;
     int *d_viscnt = nullptr;       // visual-cloud export: per (column, row chunk) counts / offsets
+    unsigned long long *d_stamps = nullptr; // gem_debug_stamps
     int *d_raylist = nullptr;      // ray clean-up: cells that cast a ray + their count
     uint32_t *d_bitmap = nullptr;  // ray clean-up: validity bitmap of the lowest layer (own tile / map-wide)
     size_t bitmap_words = 0;
@@ -120,6 +125,22 @@ struct gem_map {
 namespace {
 
 using Lock = std::lock_guard<std::recursive_mutex>;
+// k_fold_long's grid (four warps per block, one long list per warp and draw): a frame has a few hundred long lists, a
+// million-point call a few thousand
+inline int long_blocks_for(const gem_map *m, int n)
+{
+    const int b = n / 2048;
+    return b < m->long_blocks ? m->long_blocks : (b > 148 * 4 ? 148 * 4 : b);
+}
+// points per block and pass of k_fold: an even share of the call, in whole warps, at most FOLD_MARKS marks per thread
+inline int fold_slice(int n, int fold_blocks)
+{
+    int s = (n + fold_blocks - 1) / fold_blocks;
+    s = (s + 31) / 32 * 32;
+    if (s < ADD_BLOCK) s = ADD_BLOCK;
+    if (s > FOLD_MARKS * ADD_BLOCK) s = FOLD_MARKS * ADD_BLOCK;
+    return s;
+}
 
 int fail(gem_map *m, int code, const std::string &msg)
 {
@@ -184,6 +205,15 @@ inline int blocks_for(size_t n, int bs, int cap = 148 * 16)
     return (int)b;
 }
 
+// k_fold's grid: a frame-sized call gets one pass over an even share per block (at most fold_max_blocks blocks: the kernel
+// is latency bound and few fat blocks leave room for the concurrently running bin kernel); a large call gets one block
+// per full slice, scheduled in waves (a block's passes are serial latency chains, waves overlap them)
+inline int fold_blocks_for(const gem_map *m, int n)
+{
+    if ((long long)n <= (long long)m->fold_max_blocks * FOLD_MARKS * ADD_BLOCK) return blocks_for((size_t)n, ADD_BLOCK, m->fold_max_blocks);
+    return blocks_for((size_t)n, FOLD_MARKS * ADD_BLOCK, 1 << 30);
+}
+
 struct SetDev {
     int prev = -1;
     explicit SetDev(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); else prev = -1; }
@@ -243,8 +273,13 @@ int launch_regions(gem_map *m, const RegionOp *ops, int count)
 // ---- the fold of a pipelined add call is issued with the NEXT call, or here ------------------------------------
 int launch_fold(gem_map *m, cudaStream_t st, const PendingFold &p, const RegionOps &ro, int region_blocks, bool do_fuse, bool do_lowest)
 {
-    const int fb = blocks_for((size_t)p.n, ADD_BLOCK, 148 * 8);
-    GEM_LAUNCH_ON(m, st, GEM_PROF_FOLD, k_fold<<<fb + region_blocks, ADD_BLOCK, 0, st>>>(p.geom, m->ml, p.sc, p.src, ro, fb, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
+    const int fb = fold_blocks_for(m, p.n);
+    const int slice = fold_slice(p.n, fb);
+    RegionOps none{};
+    // the long lists first (their blocks claim whole SMs), then everything else; on one stream the two run back to back
+    // (disjoint cells, so the order is free) -- the frame graph of the pipelined mode runs them side by side
+    GEM_LAUNCH_ON(m, st, GEM_PROF_FOLD, k_fold_long<<<long_blocks_for(m, p.n), LONG_BLOCK, m->long_smem, st>>>(p.geom, m->ml, p.sc, p.src, none, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
+    GEM_LAUNCH_ON(m, st, GEM_PROF_FOLD, k_fold<<<fb + region_blocks, ADD_BLOCK, m->fold_smem, st>>>(p.geom, m->ml, p.sc, p.src, ro, p.n, fb, slice, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }
@@ -323,7 +358,7 @@ void pend_all_floor(gem_map *m)
 // round trips in flight instead of running 3-4 waves of serial chains
 inline int points_per_thread(int n) { return n >= 600000 ? 4 : (n >= 250000 ? 2 : 1); }
 
-typedef void (*BinKernel)(MapGeom, MapLayers, FrameParams, BinSource, int, BinScratch, RegionOps, int, const SegTable, const FrameParams *);
+typedef void (*BinKernel)(MapGeom, MapLayers, FrameParams, BinSource, int, BinScratch, const RegionOps, int, const SegTable, const FrameParams *);
 template <int SRC> BinKernel bin_kernel(int U)
 {
     if (SRC == SRC_XYZI || SRC == SRC_RECORDS) {
@@ -344,9 +379,7 @@ int read_counters(gem_map *m, long long n_in, bool accumulate)
     m->stats.points_binned += m->h_ctr->total;
     m->stats.cells_touched += m->h_ctr->ntouched;
     if (m->h_ctr->pool > m->bs[0].pool_cap) return fail(m, GEM_ERR_CUDA, "internal: record pool exhausted");
-    int mk = m->h_ctr->maxk; // only lists longer than 8 are tracked exactly
-    if (mk < 1 && m->h_ctr->ntouched > 0) mk = (m->h_ctr->total > m->h_ctr->ntouched) ? CHUNK0 : 1;
-    if (mk > m->stats.max_points_per_cell) m->stats.max_points_per_cell = mk;
+    if (m->h_ctr->maxk > m->stats.max_points_per_cell) m->stats.max_points_per_cell = m->h_ctr->maxk;
     return GEM_OK;
 }
 
@@ -423,23 +456,26 @@ int pipe_setup(gem_map *m)
 
 // {fold(previous call) || bin(this call)} as a two-node graph, built once per bin kernel; per call only the node
 // parameters change.  One cudaGraphLaunch replaces two launches, two event records and two stream waits.
-int launch_frame_graph(gem_map *m, BinKernel bk, void **bin_args, int bin_grid, void **fold_args, int fold_grid)
+int launch_frame_graph(gem_map *m, BinKernel bk, void **bin_args, int bin_grid, void **fold_args, int fold_grid, void **long_args, int long_grid)
 {
     FrameGraph &fg = m->graphs[(const void *)bk];
-    cudaKernelNodeParams kb{}, kf{};
-    kb.func = (void *)bk; kb.gridDim = dim3((unsigned)bin_grid); kb.blockDim = dim3(ADD_BLOCK); kb.sharedMemBytes = 0; kb.kernelParams = bin_args;
-    kf.func = (void *)k_fold; kf.gridDim = dim3((unsigned)fold_grid); kf.blockDim = dim3(ADD_BLOCK); kf.sharedMemBytes = 0; kf.kernelParams = fold_args;
+    cudaKernelNodeParams kb{}, kf{}, kl{};
+    kb.func = (void *)bk; kb.gridDim = dim3((unsigned)bin_grid); kb.blockDim = dim3(ADD_BLOCK); kb.sharedMemBytes = (unsigned)m->bin_smem; kb.kernelParams = bin_args;
+    kf.func = (void *)k_fold; kf.gridDim = dim3((unsigned)fold_grid); kf.blockDim = dim3(ADD_BLOCK); kf.sharedMemBytes = (unsigned)m->fold_smem; kf.kernelParams = fold_args;
+    kl.func = (void *)k_fold_long; kl.gridDim = dim3((unsigned)long_grid); kl.blockDim = dim3(LONG_BLOCK); kl.sharedMemBytes = (unsigned)m->long_smem; kl.kernelParams = long_args;
     if (!fg.exec) {
         GEM_CUDA(m, cudaGraphCreate(&fg.graph, 0));
+        GEM_CUDA(m, cudaGraphAddKernelNode(&fg.long_node, fg.graph, nullptr, 0, &kl)); // first: its blocks want empty SMs
         GEM_CUDA(m, cudaGraphAddKernelNode(&fg.fold_node, fg.graph, nullptr, 0, &kf));
         GEM_CUDA(m, cudaGraphAddKernelNode(&fg.bin_node, fg.graph, nullptr, 0, &kb));
         GEM_CUDA(m, cudaGraphInstantiate(&fg.exec, fg.graph, 0));
     } else {
+        GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(fg.exec, fg.long_node, &kl));
         GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(fg.exec, fg.fold_node, &kf));
         GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(fg.exec, fg.bin_node, &kb));
     }
     GEM_CUDA(m, cudaGraphLaunch(fg.exec, m->stream));
-    m->launches += 2;
+    m->launches += 3;
     return GEM_OK;
 }
 
@@ -466,6 +502,7 @@ int enqueue_add(gem_map *m, const BinSource &in, const FoldSrc &fsrc, int n, con
     sc.ctr = m->ctr[c];
     sc.ctr_next = m->ctr[(c + 1) % 3];
     sc.par = par;
+    sc.stamps = m->d_stamps;
     const int U = points_per_thread(n);
     BinKernel bk = bin_kernel<SRC>(U);
     const int pb = blocks_for((size_t)(n + U - 1) / U, ADD_BLOCK, 148 * 16);
@@ -489,7 +526,7 @@ int enqueue_add(gem_map *m, const BinSource &in, const FoldSrc &fsrc, int n, con
             GEM_CUDA(m, cudaStreamWaitEvent(m->front_stream, m->ev_mark, 0));
             st_bin = m->front_stream;
         }
-        GEM_LAUNCH_ON(m, st_bin, GEM_PROF_TRANSFORM_BIN, bk<<<pb + rb, ADD_BLOCK, 0, st_bin>>>(g, ml, f, bin, nn, sc, ro, pb, st, frames));
+        GEM_LAUNCH_ON(m, st_bin, GEM_PROF_TRANSFORM_BIN, bk<<<pb + rb, ADD_BLOCK, m->bin_smem, st_bin>>>(g, ml, f, bin, nn, sc, ro, pb, st, frames));
         GEM_CUDA(m, cudaGetLastError());
         commit_region_ops(m);
         if (pipelined && m->pipe_mode == 1) GEM_CUDA(m, cudaEventRecord(m->ev_bin[par], st_bin));
@@ -503,16 +540,18 @@ int enqueue_add(gem_map *m, const BinSource &in, const FoldSrc &fsrc, int n, con
         // steady state of the pipeline
         if ((rc = take_region_ops(m, ro, rb))) return rc; // row / column clears of this call's Move: executed by the previous call's fold launch
         PendingFold prev = m->pend;
-        const int fb = blocks_for((size_t)prev.n, ADD_BLOCK, 148 * 8);
+        const int fb = fold_blocks_for(m, prev.n);
+        int slice = fold_slice(prev.n, fb);
         RegionOps none{};
         if (m->pipe_mode == 2) {
             int pbk = pb, one = 1, fbk = fb;
             void *bin_args[] = {&g, &ml, &f, &bin, &nn, &sc, &none, &pbk, &st, (void *)&frames};
-            void *fold_args[] = {&prev.geom, &ml, &prev.sc, &prev.src, &ro, &fbk, &one, &one};
-            if ((rc = launch_frame_graph(m, bk, bin_args, pb, fold_args, fb + rb))) return rc;
+            void *fold_args[] = {&prev.geom, &ml, &prev.sc, &prev.src, &ro, &prev.n, &fbk, &slice, &one, &one};
+            void *long_args[] = {&prev.geom, &ml, &prev.sc, &prev.src, &none, &one, &one};
+            if ((rc = launch_frame_graph(m, bk, bin_args, pb, fold_args, fb + rb, long_args, long_blocks_for(m, prev.n)))) return rc;
         } else {
             GEM_CUDA(m, cudaStreamWaitEvent(m->front_stream, m->ev_fold[par], 0)); // the fold that last used this parity's scratch
-            GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_TRANSFORM_BIN, bk<<<pb, ADD_BLOCK, 0, m->front_stream>>>(g, ml, f, bin, nn, sc, none, pb, st, frames));
+            GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_TRANSFORM_BIN, bk<<<pb, ADD_BLOCK, m->bin_smem, m->front_stream>>>(g, ml, f, bin, nn, sc, none, pb, st, frames));
             GEM_CUDA(m, cudaEventRecord(m->ev_bin[par], m->front_stream));
             GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_bin[prev.sc.par], 0));
             if ((rc = launch_fold(m, m->stream, prev, ro, rb, true, true))) return rc;
@@ -613,13 +652,17 @@ int gem_create(const gem_config *cfg, gem_map **out)
     m->geom.c0 = tiled ? cfg->tile_col0 : 0;
     m->geom.cols = tiled ? cfg->tile_cols : m->L;
     m->nc = (size_t)m->geom.rows * m->geom.cols;
-    m->P = cfg->max_points > 0 ? cfg->max_points : (1 << 21);
+    m->P = cfg->max_points > 0 ? cfg->max_points : (1 << 20); // per point: 16 B mark + 528 B level-1 chunk space, x 2 parities
     // the fold's sort key packs the point index of a launch into 22 bits; larger calls are chunked
     if (m->P > (1 << FOLD_INDEX_BITS)) m->P = 1 << FOLD_INDEX_BITS;
     {
         const char *env = getenv("GEM_B200_PIPE"); // graph (default) | stream | off
         if (env && !strcmp(env, "stream")) m->pipe_mode = 1;
         else if (env && !strcmp(env, "off")) m->pipe_mode = 0;
+        const char *e1 = getenv("GEM_B200_FOLD_BLOCKS"), *e2 = getenv("GEM_B200_LONG_BLOCKS"), *e3 = getenv("GEM_B200_EXCLUSIVE");
+        if (e1 && atoi(e1) > 0) m->fold_max_blocks = atoi(e1);
+        if (e2 && atoi(e2) > 0) m->long_blocks = atoi(e2);
+        if (e3 && atoi(e3) == 1) { m->bin_smem = BIN_SMEM_BYTES; m->fold_smem = FOLD_SMEM_BYTES; m->long_smem = LONG_SMEM_BYTES; }
     }
 
     int rc = GEM_OK;
@@ -636,7 +679,7 @@ int gem_create(const gem_config *cfg, gem_map **out)
         if (e != cudaSuccess) { m->err = cudaGetErrorString(e); return bail(GEM_ERR_CUDA); }
         m->own_stream = true;
     }
-    const size_t nc = m->nc, P = (size_t)m->P, T = P < nc ? P : nc;
+    const size_t nc = m->nc, P = (size_t)m->P;
     if ((rc = dev_alloc(m, &m->ml.cell, nc)) || (rc = dev_alloc(m, &m->ml.traver, nc)) || (rc = dev_alloc(m, &m->ml.lowest, nc)) ||
         (rc = dev_alloc(m, &m->ml.rough, nc)) || (rc = dev_alloc(m, &m->ml.slope, nc)) || (rc = dev_alloc(m, &m->ml.traver_out, nc)) ||
         (rc = dev_alloc(m, &m->ctr[0], 3)))
@@ -646,13 +689,15 @@ int gem_create(const gem_config *cfg, gem_map **out)
     for (int p = 0; p < 2; p++) {
         BinScratch &sc = m->bs[p];
         sc.par = p;
-        // every cell with k >= 9 records takes at most 4k + 8 pool slots (chunks of 32, 128, ... records + headers)
+        // only cells with more than 40 records take pool chunks: at most 4k + 12 slots for a cell of k records
         sc.pool_cap = (int)std::min<size_t>(5 * P + 64, (size_t)0x7ffffff0);
-        if ((rc = dev_alloc(m, &sc.touched, T)) || (rc = dev_alloc(m, &sc.chunk0, (size_t)CHUNK0 * T)) || (rc = dev_alloc(m, &sc.ovf1, T)) ||
-            (rc = dev_alloc(m, &sc.pool, (size_t)sc.pool_cap + 1)) || (rc = dev_alloc(m, &sc.tlarge, list_cap(P, nc, CHUNK0))) ||
+        if ((rc = dev_alloc(m, &sc.mark, P)) || (rc = dev_alloc(m, &sc.chunk0, (size_t)CHUNK0 * nc)) ||
+            (rc = dev_alloc(m, &sc.pool1, (size_t)CHUNK1_SLOTS * P)) || (rc = dev_alloc(m, &sc.pool, (size_t)sc.pool_cap + 1)) ||
             (rc = dev_alloc(m, &sc.tlong, list_cap(P, nc, FOLD_LONG_FROM))))
             return bail(rc);
-        e = cudaMemsetAsync(sc.ovf1, 0, T * sizeof(int), m->stream);
+        // no stale chunk headers (the fold clears the ones it consumes); records and marks need no initialisation
+        e = cudaMemsetAsync(sc.pool1, 0, (size_t)CHUNK1_SLOTS * P * sizeof(uint4), m->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(sc.pool, 0, ((size_t)sc.pool_cap + 1) * sizeof(uint4), m->stream);
         if (e != cudaSuccess) { m->err = cudaGetErrorString(e); return bail(GEM_ERR_CUDA); }
     }
     e = cudaHostAlloc((void **)&m->h_ctr, sizeof(BinCounters), cudaHostAllocDefault);
@@ -669,6 +714,9 @@ int gem_create(const gem_config *cfg, gem_map **out)
         m->err = std::string("gem_create: init kernels failed (is the device sm_100?): ") + cudaGetErrorString(e);
         return bail(GEM_ERR_NO_DEVICE);
     }
+    e = cudaFuncSetAttribute(k_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOLD_SMEM_BYTES); // > 48 KB: opt-in
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fold_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LONG_SMEM_BYTES);
+    if (e != cudaSuccess) { m->err = std::string("gem_create: k_fold shared memory: ") + cudaGetErrorString(e); return bail(GEM_ERR_CUDA); }
     pend_all_floor(m); // first Fuse floors every cell (gpu.cu:533-534)
     *out = m;
     return GEM_OK;
@@ -711,6 +759,24 @@ int gem_destroy(gem_map *m)
 }
 
 void *gem_get_stream(gem_map *m) { return m ? (void *)m->stream : nullptr; }
+
+int gem_debug_stamps(gem_map *m, int enable, unsigned long long out[16])
+{
+    if (!m) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
+    SetDev sd(m->dev);
+    int rc = drain(m);
+    if (rc) return rc;
+    if (out && m->d_stamps) {
+        GEM_CUDA(m, cudaMemcpyAsync(out, m->d_stamps, 16 * 8, cudaMemcpyDeviceToHost, m->stream));
+        GEM_CUDA(m, cudaStreamSynchronize(m->stream));
+        out[0] = ~out[0]; out[8] = ~out[8];
+    }
+    if (enable && !m->d_stamps && (rc = dev_alloc(m, &m->d_stamps, 16))) return rc;
+    if (m->d_stamps) GEM_CUDA(m, cudaMemsetAsync(m->d_stamps, 0, 16 * 8, m->stream));
+    if (!enable) m->d_stamps = nullptr; // (the 128 bytes stay allocated until gem_destroy)
+    return GEM_OK;
+}
 
 int gem_flush(gem_map *m)
 {
@@ -836,7 +902,7 @@ int gem_add_points(gem_map *m, const void *xyzi, const void *rgba, int n, const 
     for (int off = 0; off < n; off += m->P) {
         const int cn = (n - off < m->P) ? (n - off) : m->P;
         const BinSource in = xyzi_source(xyzi, rgba, off);
-        const FoldSrc fs{SRC_XYZI, in.xyzi};
+        const FoldSrc fs{in.xyzi ? (const char *)in.xyzi + 12 : nullptr, 16};
         if ((rc = enqueue_add<SRC_XYZI>(m, in, fs, cn, fp, nullptr, nullptr, false, true, true))) return rc;
         if (n > m->P && (rc = read_counters(m, cn, true))) return rc; // chunked: keep totals
     }
@@ -861,7 +927,7 @@ int gem_add_points_host(gem_map *m, const void *xyzi, const void *rgba, int n, c
         if (rgba)
             GEM_CUDA(m, cudaMemcpyAsync(m->d_rgba, (const uchar4 *)rgba + off, (size_t)cn * 4, cudaMemcpyHostToDevice, m->stream));
         const BinSource in = xyzi_source(m->d_xyzi, rgba ? m->d_rgba : nullptr, 0);
-        const FoldSrc fs{SRC_XYZI, in.xyzi};
+        const FoldSrc fs{in.xyzi ? (const char *)in.xyzi + 12 : nullptr, 16};
         if ((rc = enqueue_add<SRC_XYZI>(m, in, fs, cn, fp, nullptr, nullptr, false, true, true))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc; // also the host-visible completion point
     }
@@ -877,7 +943,7 @@ int gem_add_points_stream(gem_map *m, const void *xyzi, const void *rgba, int n,
     if (n == 0) return flush_all_pending(m);
     const FrameParams fp = make_frame(frame);
     const BinSource in = xyzi_source(xyzi, rgba, 0);
-    const FoldSrc fs{SRC_XYZI, in.xyzi};
+    const FoldSrc fs{in.xyzi ? (const char *)in.xyzi + 12 : nullptr, 16};
     int rc = enqueue_add<SRC_XYZI>(m, in, fs, n, fp, nullptr, nullptr, true, true, true);
     if (rc) return rc;
     memset(&m->stats, 0, sizeof m->stats);
@@ -912,7 +978,7 @@ int gem_add_points_multi(gem_map *m, const void *xyzi, const void *rgba, int n_s
     GEM_CUDA(m, cudaMemcpyAsync(df, hf, (size_t)n_segments * sizeof(FrameParams), cudaMemcpyHostToDevice, m->stream));
     GEM_CUDA(m, cudaEventRecord(m->ev_frames[slot], m->stream));
     const BinSource in = xyzi_source(xyzi, rgba, 0);
-    const FoldSrc fs{SRC_XYZI, in.xyzi};
+    const FoldSrc fs{in.xyzi ? (const char *)in.xyzi + 12 : nullptr, 16};
     // pipelined like gem_add_points_stream: consecutive multi-sensor steps overlap bin(i+1) with fold(i)
     if ((rc = enqueue_add<SRC_XYZI>(m, in, fs, n, hf[0], &st, df, true, true, true))) return rc;
     memset(&m->stats, 0, sizeof m->stats);
@@ -953,7 +1019,7 @@ int gem_add_points_host_async(gem_map *m, const void *xyzi, const void *rgba, in
     if (m->pipe_mode == 1 && m->front_stream) GEM_CUDA(m, cudaStreamWaitEvent(m->front_stream, m->ev_h2d[b], 0));
     const FrameParams fp = make_frame(frame);
     const BinSource in = xyzi_source(m->d_axyzi[b], rgba ? m->d_argba[b] : nullptr, 0);
-    const FoldSrc fs{SRC_XYZI, in.xyzi};
+    const FoldSrc fs{in.xyzi ? (const char *)in.xyzi + 12 : nullptr, 16};
     BinCounters *prev_ctr = m->pend.active ? m->pend.sc.ctr : nullptr;
     if ((rc = enqueue_add<SRC_XYZI>(m, in, fs, n, fp, nullptr, nullptr, true, true, true))) return rc;
     // the step's host-visible result: the counters of the newest call whose fold has been issued
@@ -982,7 +1048,7 @@ int gem_add_cloud_pcl_host(gem_map *m, const void *pts, int n, const gem_frame *
         GEM_CUDA(m, cudaMemcpyAsync(m->d_pcl, (const char *)pts + (size_t)off * 32, (size_t)cn * 32, cudaMemcpyHostToDevice, m->stream));
         BinSource in{};
         in.pcl = (const float4 *)m->d_pcl;
-        const FoldSrc fs{SRC_PCL32, in.pcl};
+        const FoldSrc fs{(const char *)in.pcl + 24, 32};
         if ((rc = enqueue_add<SRC_PCL32>(m, in, fs, cn, fp, nullptr, nullptr, false, true, true))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc;
     }
@@ -1016,7 +1082,7 @@ int gem_process_points(gem_map *m, int *map_index, const float *x, const float *
         BinSource in{};
         in.x = m->d_x; in.y = m->d_y; in.z = m->d_z;
         in.key_out = m->d_keyout; in.h_out = m->d_h; in.hv_out = m->d_hv; in.xt_out = m->d_xt; in.yt_out = m->d_yt;
-        const FoldSrc fs{SRC_SOA, nullptr};
+        const FoldSrc fs{nullptr, 0};
         if ((rc = enqueue_add<SRC_SOA>(m, in, fs, cn, fp, nullptr, nullptr, false, false, true))) break; // lowest-scan only
         if (map_index && e == cudaSuccess) e = cudaMemcpyAsync(map_index + off, m->d_keyout, b, cudaMemcpyDeviceToHost, m->stream);
         if (var && e == cudaSuccess) e = cudaMemcpyAsync(var + off, m->d_hv, b, cudaMemcpyDeviceToHost, m->stream);
@@ -1056,7 +1122,7 @@ int gem_fuse(gem_map *m, int n, const int *index, const int *R, const int *G, co
             GEM_CUDA(m, cudaMemcpyAsync(m->d_int, intensity + off, b, cudaMemcpyHostToDevice, m->stream));
             in.inten_in = m->d_int;
         }
-        const FoldSrc fs{SRC_KEYS, in.inten_in};
+        const FoldSrc fs{(const char *)in.inten_in, 4};
         const FrameParams none{};
         if ((rc = enqueue_add<SRC_KEYS>(m, in, fs, cn, none, nullptr, nullptr, false, true, false))) return rc;
         if ((rc = read_counters(m, cn, true))) return rc;
@@ -1551,7 +1617,7 @@ static int fuse_records_impl(gem_map *m, const void *rec, int n, const int *src_
         in.rec = (const RouteRec *)rec + off;
         in.src_counts = src_counts; // counted buffers are never chunked (n <= max_points is checked by the caller)
         in.stride = stride;
-        const FoldSrc fs{SRC_RECORDS, in.rec};
+        const FoldSrc fs{(const char *)in.rec + 16, (int)sizeof(RouteRec)};
         const FrameParams none{};
         if ((rc = enqueue_add<SRC_RECORDS>(m, in, fs, cn, none, nullptr, nullptr, false, true, true))) return rc;
         if (n > m->P && (rc = read_counters(m, cn, true))) return rc;

@@ -163,6 +163,11 @@ class ElevationMap:
         import torch
         return torch.cuda.ExternalStream(self.cuda_stream)
 
+    def debug_stamps(self, enable=True):
+        out = (C.c_ulonglong * 16)()
+        check(self._lib.gem_debug_stamps(self._h, 1 if enable else 0, out), self._h, "gem_debug_stamps")
+        return [int(v) for v in out]
+
     def flush(self):
         """enqueue the work the pipelined add calls deferred (no host wait)"""
         check(self._lib.gem_flush(self._h), self._h, "gem_flush")

@@ -129,6 +129,11 @@ void *gem_get_stream(gem_map *m);
  * _multi / _host_async call) on the handle's stream without waiting for it; gem_sync and every call that
  * reads or changes the map do this implicitly */
 int gem_flush(gem_map *m);
+/* debug: %globaltimer marks (ns) of the add kernels' phases, accumulated since the last call (min of the starts,
+ * max of the marks): [0] k_bin start, [1] ranks drawn, [2] slots reserved, [3] pointers published, [4] records
+ * stored; [8] k_fold start, [9] long + large lists done, [10] short lists done, [11] longest lists loaded,
+ * [12] longest lists folded.  enable != 0 (re)arms the marks, 0 disarms them; out may be NULL. */
+int gem_debug_stamps(gem_map *m, int enable, unsigned long long out[16]);
 
 /* Move (gpu.cu:1004-1083): scroll the circular buffer to follow pos[0..1], record
  * pos[2] as sensorZatLowestScan.  Outputs may be NULL. */

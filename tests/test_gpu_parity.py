@@ -585,6 +585,56 @@ def test_large_grid_4096_config4_size():
     assert_layers_equal(g, o, what="4096^2 second frame")
 
 
+def test_c5_size_8192_frame_and_multi_sensor_vs_oracle():
+    """BASELINE config 5 map size (8192x8192 @ 0.05 m, 2.1 GB of cells) on one GPU: one frame against the oracle, then
+    gem_add_points_multi (8 sensors on the SURVEY rig, one launch) against the oracle fed the same eight clouds.  The
+    fused layers of the multi call equal eight sequential adds; `lowest` is one call's minimum (ORACLE DEFINITION,
+    DESIGN.md section 5) and is checked against a numpy evaluation of that definition from the oracle's per-point outputs."""
+    import torch
+    from gem_b200 import tiled
+    L, res = 8192, 0.05
+    fr = synth.hdl64_frame(3)
+    f = laser_frame(fr["T"])
+    g, o = both(L, res, compat_box_filter=False)
+    for m in (g, o):
+        m.add(fr["xyzi"], fr["rgba"], f)
+    assert_layers_equal(g, o, what="8192^2 one frame")
+    scene = synth.make_scene()
+    frs = [synth.hdl64_frame(20 + k, scene=scene) for k in range(8)]
+    fobj = []
+    for k, fr8 in enumerate(frs):
+        T = fr8["T"].copy()
+        T[0, 3], T[1, 3] = tiled.sensor_offset(k, 8)
+        fobj.append(laser_frame(T))
+    x = torch.from_numpy(np.concatenate([q["xyzi"] for q in frs])).cuda()
+    c = torch.from_numpy(np.concatenate([q["rgba"] for q in frs])).cuda()
+    off = np.concatenate([[0], np.cumsum([q["xyzi"].shape[0] for q in frs])])
+    torch.cuda.synchronize()
+    low0 = o.get_layer("lowest").reshape(-1).copy()
+    g.add_multi(x, c, off, fobj)
+    keys, hs, hvs = [], [], []
+    for q, fq in zip(frs, fobj):   # oracle: the same clouds in order (per-cell order = global point index)
+        key, var, _, _, zt = o.process_points(q["xyzi"][:, 0], q["xyzi"][:, 1], q["xyzi"][:, 2], fq)
+        R, G, B = (q["rgba"][:, k].astype(np.int32) for k in range(3))
+        o.fuse_points(key, R, G, B, q["xyzi"][:, 3], zt, var)
+        keys.append(key); hs.append(zt); hvs.append(var)
+    assert_layers_equal(g, o, ["elevation", "variance", "intensity", "color_r", "color_g", "color_b"], what="8192^2 multi-sensor")
+    assert g.stats()["points_in"] == int(off[-1])
+    # lowest of ONE call over all eight clouds (start index is 0: storage key == geographic index)
+    key, h, hv = np.concatenate(keys), np.concatenate(hs), np.concatenate(hvs)
+    ok = key >= 0
+    key, h, hv = key[ok], h[ok], hv[ok]
+    order = np.lexsort((np.arange(key.size), h, key))       # per cell: lowest height first, first index among equals
+    first = np.ones(key.size, bool)
+    first[1:] = key[order][1:] != key[order][:-1]
+    ck, cm, cv = key[order][first], h[order][first], hv[order][first]
+    expect = low0.copy()
+    upd = cm <= low0[ck]
+    expect[ck[upd]] = (cm[upd] + np.float32(3.0) * cv[upd]).astype(np.float32)
+    got = g.get_layer("lowest").reshape(-1)
+    assert np.array_equal(got.view(np.uint32), expect.view(np.uint32)), int((got != expect).sum())
+
+
 def test_error_paths_return_codes():
     import ctypes as C
     from gem_b200 import _lib
