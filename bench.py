@@ -158,13 +158,13 @@ def best_cpu_threads(frames, L: int, res: float):
     cands = sorted({t for t in (8, 16, 32, 64, ncpu) if t <= ncpu} | {min(ncpu, 8)})
     best, best_v = cands[0], -1.0
     for t in cands:
-        v, _, _ = cpu_baseline(frames, 4, t, L, res)
+        v, _, _ = cpu_baseline(frames, 4, t, L, res, warmup=1)
         if v > best_v:
             best, best_v = t, v
     return best
 
 
-def cpu_baseline(frames, nsteps: int, threads: int, L: int, res: float):
+def cpu_baseline(frames, nsteps: int, threads: int, L: int, res: float, warmup: int = 3):
     """CPU oracle (restatement of the reference semantics; the reference ships no CPU path) on
     `threads` host threads over the same stream.  Returns (Mpoints/s, ms/frame, n_frames)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -172,14 +172,14 @@ def cpu_baseline(frames, nsteps: int, threads: int, L: int, res: float):
     o = OracleMap(L, res, compat_box_filter=False)
     F = len(frames)
     fobjs = [laser_frame(fr) for fr in frames]
-    for s in range(min(3, nsteps)):  # warm-up
+    for s in range(warmup):  # warm-up
         k = pingpong(s, F)
         o.move(frames[k]["position"])
         o.add_mt(frames[k]["xyzi"], frames[k]["rgba"], fobjs[k], threads)
     pts = 0
     t0 = time.perf_counter()
     for s in range(nsteps):
-        k = pingpong(3 + s, F)
+        k = pingpong(warmup + s, F)
         o.move(frames[k]["position"])
         o.add_mt(frames[k]["xyzi"], frames[k]["rgba"], fobjs[k], threads)
         pts += frames[k]["xyzi"].shape[0]
@@ -188,19 +188,28 @@ def cpu_baseline(frames, nsteps: int, threads: int, L: int, res: float):
     return pts / dt / 1e6, dt / nsteps * 1e3, nsteps
 
 
+WORKLOAD_C2 = "configs[1]: HDL-64E-shaped synthetic 10 Hz stream into 1024x1024@0.05m robot-centric map, 1xB200"
+
+
+def workload_tiled(N, L):
+    return (f"{N} HDL-64E-shaped sensors (one per GPU) into one {L}x{L}@0.05m global map tiled across {N}xB200, "
+            "points routed to the owning tile over NVLink (configs[3]/[4] shape)")
+
+
 # ------------------------------------------------------------------------------------------
 def run_reference(args):
-    """Reference arm.  The reference has no CPU implementation of this path (and its CUDA file is
-    not a CPU program), so this times the CPU oracle -- the restatement of the reference semantics,
-    pinned against the reference's own kernels -- on the host threads, on the same workload as the
-    gem_b200 arm at this --gpus value.  For N > 1 (tiled workload: N sensors into a (1024 N)^2 map)
-    each step is a bounded sample: sensor 0's cloud of that step, i.e. 1/N of the step's points."""
+    """Reference arm.  The reference has no CPU implementation of this path (and its CUDA file is not a CPU program),
+    so this times the CPU oracle -- the restatement of the reference semantics, pinned against the reference's own
+    kernels -- on the host threads, on the SAME workload as the gem_b200 arm at this --gpus value: same frame set
+    (--frames distinct frames, cycled the same way), same number of warm-up and timed steps.  For N > 1 (tiled
+    workload: N sensors into a (1024 N)^2 map) each step is a bounded sample: sensor 0's cloud of that step, i.e. 1/N
+    of the step's points."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
     N = max(1, args.gpus)
     L, res = 1024 * N, 0.05
-    F = max(2, min(args.steps + args.warmup + 3, 16))
+    F = int(max(2, args.frames))
     frames = gen_frames(F)
     if N > 1:   # same rig geometry as gem_b200/tiled.py: sensor 0 of the rig, 1 m per step along +x
         from gem_b200 import tiled
@@ -210,20 +219,20 @@ def run_reference(args):
             T[0, 3], T[1, 3] = ox + (k - F / 2.0), oy
             fr["T"] = T
             fr["position"] = np.array([0.0, 0.0, T[2, 3]])   # global map: no scroll
-    nsteps = max(1, args.steps)
-    threads = best_cpu_threads(frames, L, res)
-    o_val, ms, n = cpu_baseline(frames, nsteps, threads, L, res)
+    nsteps, W = max(1, args.steps), max(0, args.warmup)
+    threads = best_cpu_threads(frames[: min(F, 16)], L, res)
+    o_val, ms, n = cpu_baseline(frames, nsteps, threads, L, res, warmup=W)
     ppf = float(np.mean([f["xyzi"].shape[0] for f in frames]))
     metric = "Mpoints/s fused into 1024x1024@0.05m grid" if N == 1 else "Mpoints/s fused into tiled grid"
     sample = (f"{n} frames of the c2 stream, oracle process_points+fuse, {threads} threads" if N == 1 else
               f"{n} steps, sensor 0's cloud only (1/{N} of each step's points) into the same {L}x{L} map, {threads} threads")
     line = {
         "impl": "reference", "metric": metric, "value": o_val,
-        "unit": "Mpoints/s", "n_gpus": args.gpus, "steps": n, "warmup": 3, "ms_per_step": ms,
+        "unit": "Mpoints/s", "n_gpus": args.gpus, "steps": n, "warmup": W, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": ("configs[1]: HDL-64E-shaped synthetic 10 Hz stream into 1024x1024@0.05m map" if N == 1 else
-                                f"{N} HDL-64E-shaped sensors into one {L}x{L}@0.05m global map (configs[3]/[4] shape)"),
-                   "points_per_frame": ppf,
+        "config": {"workload": WORKLOAD_C2 if N == 1 else workload_tiled(N, L),
+                   "points_per_frame": ppf, "distinct_frames": F, "box_filter": "off (SURVEY 8d documented deviation)",
+                   "colour_path": True,
                    "note": "the reference ships no CPU path; this arm times the CPU oracle port of its semantics "
                            "(oracle/gem_oracle.c, pinned against the reference's kernels, DESIGN.md section 6)"},
         "cpu_baseline": {"value": o_val, "unit": "Mpoints/s", "cores": threads, "kind": "port", "sample": sample},
@@ -231,6 +240,101 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     return line
+
+
+def time_reference_gpu_kernels(frames, fobjs, L, res, nsteps=12):
+    """extra.reference_gpu_kernels: the reference's OWN Process_points + Fuse wrappers (oracle/_ref = gpu_process.cu
+    compiled unmodified against the stand-in Eigen header, with the reference's flags) on this GPU, host arrays in /
+    out like the node calls them (per-call cudaMalloc/cudaMemcpy/cudaFree included: that is the reference's design).
+    Wall clock per frame.  What libgem_b200 replaces."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_lib
+    if not ref_lib.available(nofma=False):
+        return {"unavailable": "oracle/_ref/libgpu_ref.so not built (needs /root/reference at build time)"}
+    r = ref_lib.RefMap(L, res, nofma=False)
+    F = len(frames)
+    t_pp = t_fu = 0.0
+    pts = 0
+    for s in range(nsteps + 2):
+        k = s % F
+        fr = frames[k]
+        x, y, z = (np.ascontiguousarray(fr["xyzi"][:, i]) for i in range(3))
+        R, G, B = (fr["rgba"][:, i].astype(np.int32) for i in range(3))
+        inten = np.ascontiguousarray(fr["xyzi"][:, 3])
+        r.move(fr["position"])
+        t0 = time.perf_counter()
+        key, var, xt, yt, zt = r.process_points(x, y, z, fobjs[k])
+        t1 = time.perf_counter()
+        r.fuse_points(key, R, G, B, inten, zt, var)
+        t2 = time.perf_counter()
+        if s >= 2:
+            t_pp += t1 - t0; t_fu += t2 - t1; pts += x.shape[0]
+    return {"process_points_ms": t_pp / nsteps * 1e3, "fuse_ms": t_fu / nsteps * 1e3,
+            "value": pts / (t_pp + t_fu) / 1e6, "unit": "Mpoints/s", "frames": nsteps, "grid": f"{L}x{L}@{res}",
+            "what": "reference gpu_process.cu Process_points + Fuse (O(cells x points) G_fuse), host-array interface, wall clock"}
+
+
+def run_c3(K=150):
+    """extra.c3: BASELINE configs[2] -- D435 640x480 raw depth frames (307 200 points, NaN / out-of-range depths left
+    in: the structured-light pass-through is part of the path) into a 512x512@0.02m map, frame pipeline."""
+    import ctypes as C
+    import torch
+    import gem_b200
+    from gem_b200 import synth
+    dev = torch.device("cuda", 0)
+    frames = [synth.d435_frame(k) for k in range(8)]
+    sp = gem_b200.StructuredLightSensorProcessor()
+    fobjs = [gem_b200.make_frame(fr["T"], sp, base_z=0.0) for fr in frames]
+    m = gem_b200.ElevationMap(512, 0.02, compat_box_filter=False)
+    st = m.torch_stream()
+    xd = [torch.from_numpy(fr["xyzi"]).to(dev) for fr in frames]
+    rd = [torch.from_numpy(fr["rgba"]).to(dev) for fr in frames]
+    pos_c = [(C.c_float * 3)(*[float(v) for v in fr["position"]]) for fr in frames]
+    n = frames[0]["xyzi"].shape[0]
+
+    def step(s):
+        k = pingpong(s, len(frames))
+        m.move_fast(pos_c[k])
+        m.add_stream_fast(C.c_void_p(xd[k].data_ptr()), C.c_void_p(rd[k].data_ptr()), n, C.byref(fobjs[k]))
+    for s in range(20):
+        step(s)
+    m.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for s in range(K):
+        step(20 + s)
+    m.flush()
+    e1.record(st)
+    m.sync()
+    ms = e0.elapsed_time(e1)
+    stt = m.stats()
+    m.close()
+    return {"workload": "configs[2]: RealSense-D435 640x480 raw depth frames (307 200 points/frame, structured-light model + "
+                        "depth pass-through) into 512x512@0.02m, 1xB200", "value": n * K / (ms * 1e-3) / 1e6, "unit": "Mpoints/s",
+            "ms_per_step": ms / K, "frames_per_s": K / (ms * 1e-3), "last_frame_stats": stt}
+
+
+def cpu_baseline_c1(threads):
+    """the CPU baseline on BASELINE configs[0] (one 64-beam frame into 200x200@0.1m)."""
+    from gem_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import OracleMap
+    fr = synth.hdl64_frame(0)
+    f = laser_frame(fr)
+    out = {}
+    for nt in (1, threads):
+        o = OracleMap(200, 0.1, compat_box_filter=False)
+        o.move(fr["position"])
+        o.add_mt(fr["xyzi"], fr["rgba"], f, nt)        # warm-up (first-touch of the layers)
+        reps = 20
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            o.add_mt(fr["xyzi"], fr["rgba"], f, nt)
+        dt = (time.perf_counter() - t0) / reps
+        o.close()
+        out[f"threads_{nt}"] = {"value": fr["xyzi"].shape[0] / dt / 1e6, "unit": "Mpoints/s", "ms_per_frame": dt * 1e3}
+    out["workload"] = "configs[0]: single synthetic 64-beam frame into 200x200@0.1m, CPU oracle port (the reference has no CPU add)"
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -313,7 +417,8 @@ def run_single(args):
     s0 += K
     value = pts / (ms_total * 1e-3) / 1e6
 
-    # ---- per-kernel durations (separate pass: event bracketing perturbs the timeline) ----------
+    # ---- per-kernel durations: a SERIAL pass (gem_profile_enable makes the add calls issue bin -> fold_long -> fold
+    # one after the other on one stream, each bracketed by CUDA events: no overlap, so the figures are uncontended) ----
     Kp = min(K, 200)
     m.profile_enable(True)
     ppts = 0
@@ -322,22 +427,28 @@ def run_single(args):
     prof = m.profile_read(reset=True)
     m.profile_enable(False)
     s0 += Kp
-    add_classes = ["transform_bin", "fold", "clear_floor"]
-    dom = max(add_classes, key=lambda c: prof["ms"][c])
-    dom_avg_ms = prof["ms"][dom] / max(1, prof["count"][dom])
+    add_classes = ["bin", "fold_long", "fold", "clear_floor"]
+    kname = {"bin": "k_bin", "fold_long": "k_fold_long", "fold": "k_fold", "clear_floor": "k_regions"}
+    avg_us = {c: prof["ms"][c] / max(1, prof["count"][c]) * 1e3 for c in add_classes}
+    dom = max(add_classes, key=lambda c: avg_us[c])
+    dom_avg_ms = avg_us[dom] * 1e-3
     peak, peak_src = load_peaks()
     algo_bytes = ALGO_BYTES_PER_POINT * (ppts / Kp)
     achieved = algo_bytes / (dom_avg_ms * 1e-3) / 1e9
-    step_ms_prof = sum(prof["ms"][c] for c in add_classes) / Kp
+    tot_ms = sum(prof["ms"][c] for c in add_classes)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": load_traffic({"transform_bin": "k_bin", "fold": "k_fold", "clear_floor": "k_regions"}[dom]),
-        "kernel": dom, "kernel_avg_us": dom_avg_ms * 1e3, "peak_source": peak_src,
+        "traffic": load_traffic(kname[dom]),
+        "kernel": kname[dom], "kernel_avg_us": avg_us[dom], "peak_source": peak_src,
+        "kernel_time_source": "serial profiling pass of this run (events around every launch, nothing overlapped); "
+                              "the committed ncu launch list profiles/r2_launches_summary.txt gives the same ranking",
         "algorithmic_bytes_per_launch": algo_bytes,
         "whole_step": {"achieved": algo_bytes / (ms_total / K * 1e-3) / 1e9,
                        "frac": algo_bytes / (ms_total / K * 1e-3) / 1e9 / peak},
-        "kernel_share_of_step": {c: prof["ms"][c] / max(1e-12, sum(prof["ms"][x] for x in add_classes)) for c in add_classes},
-        "kernel_us_per_step": {c: prof["ms"][c] / Kp * 1e3 for c in add_classes},
+        "kernel_share_of_step": {kname[c]: prof["ms"][c] / max(1e-12, tot_ms) for c in add_classes},
+        "kernel_us_per_launch": {kname[c]: avg_us[c] for c in add_classes},
+        "note": "a c2 frame is 5.4 MB of algorithmic traffic (0.8 us at the HBM peak): the kernels are bound by dependent "
+                "L2 round trips and the serial fold of the longest per-cell list, not by bandwidth (DESIGN.md section 4)",
     }
 
     # ---- e2e: host (pinned) buffers through the public API, H2D + D2H inside the timed region ------
@@ -346,8 +457,6 @@ def run_single(args):
         k = pingpong(s0, F); m.move(pos[k]); m.add(xyzi_h[k].numpy(), rgba_h[k].numpy(), fobjs[k]); s0 += 1
     torch.cuda.synchronize()
     epts = 0
-    xh = [t.numpy() for t in xyzi_h]
-    rh = [t.numpy() for t in rgba_h]
     t0 = time.perf_counter()
     e0.record(stream)
     for s in range(Ke):
@@ -361,7 +470,7 @@ def run_single(args):
     s0 += Ke
     e2e_sync_value = epts / (e2e_ms * 1e-3) / 1e6
     # pipelined variant of the same public call: H2D of frame i+1 overlaps the kernels of frame i
-    # (two staging buffers, copy stream); every step still does its own H2D and its counters D2H
+    # (three staging buffers, copy stream); every step still does its own H2D and a counters D2H
     for s in range(4):
         k = pingpong(s0, F); m.move_fast(pos_c[k]); m.add_host_async_fast(xhptr[k], rhptr[k], npts[k], fref[k]); s0 += 1
     m.sync()
@@ -380,50 +489,77 @@ def run_single(args):
     torch.cuda.synchronize()
     a_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
     s0 += Ke
-    ctr_bytes = 640
+    ctr_bytes = 768
     e2e = {"value": apts / (a_ms * 1e-3) / 1e6, "unit": "Mpoints/s",
            "h2d_bytes_per_step": 20.0 * apts / Ke, "d2h_bytes_per_step": ctr_bytes,
            "api": "gem_move + gem_add_points_host_async (pinned host xyzi+rgba in via copy stream, counters out; "
                   "wall clock incl. final sync)",
            "host_synchronous_variant": {"value": e2e_sync_value, "api": "gem_move + gem_add_points_host (sync per frame)"}}
 
-    # ---- whole frame incl. features + ray clean-up + grid_map write-back (secondary) --------------
-    Kf = min(K, 20)
+    # ---- e2e_frame: what a node waits for per sensor frame, through the public calls, from 32-byte PCL records in
+    # pinned host memory: Move + add (gem_add_cloud_pcl_host: H2D + bin + fold) + Mapvar_update + Map_feature's kernel
+    # + grid_map write-back (9 layers into pinned host memory) + Raytracing ----
+    Kf = min(K, 30)
+    pcl_h = []
+    for fr in frames[: min(F, 8)]:
+        rec = np.zeros((fr["xyzi"].shape[0], 8), np.float32)
+        rec[:, :3] = fr["xyzi"][:, :3]; rec[:, 3] = 1.0
+        bgra = np.stack([fr["rgba"][:, 2], fr["rgba"][:, 1], fr["rgba"][:, 0], np.full(fr["rgba"].shape[0], 255, np.uint8)], 1)
+        rec[:, 4] = np.ascontiguousarray(bgra).view(np.float32).reshape(-1)
+        rec[:, 6] = fr["xyzi"][:, 3]
+        pcl_h.append(torch.from_numpy(rec).pin_memory())
     ex_pin = {n: torch.empty((L, L), dtype=torch.float32).pin_memory() for n in gem_b200._lib.EXPORT_LAYERS}
     ex = {n: ex_pin[n].numpy().T for n in ex_pin}   # column-major views of pinned host memory
+    for s in range(3):
+        k = pingpong(s0 + s, F) % len(pcl_h)
+        m.move(pos[k]); m.add_pcl(pcl_h[k].numpy(), fobjs[k]); m.var_update(0.0); m.compute_features(); m.export_layers(ex); m.raytracing()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for s in range(Kf):
-        k = pingpong(s0 + s, F)
-        m.move(pos[k]); m.add(xyzi_d[k], rgba_d[k], fobjs[k], n=npts[k])
+        k = pingpong(s0 + 3 + s, F) % len(pcl_h)
+        m.move(pos[k]); m.add_pcl(pcl_h[k].numpy(), fobjs[k])
         m.var_update(0.0); m.compute_features(); m.export_layers(ex); m.raytracing()
     torch.cuda.synchronize()
     frame_ms = (time.perf_counter() - t0) * 1e3 / Kf
+    e2e_frame = {"ms_per_frame": frame_ms, "frames": Kf,
+                 "api": "gem_move + gem_add_cloud_pcl_host (32 B PointXYZRGBICT records from pinned host memory) + gem_var_update + "
+                        "gem_compute_features + gem_export_layers (9 column-major layers into pinned host memory) + gem_raytracing, "
+                        "host-synchronous like the node",
+                 "h2d_bytes_per_frame": 32.0 * float(np.mean(npts)), "d2h_bytes_per_frame": 9 * 4 * L * L}
     clocks = sampler.stop()
 
     # ---- secondary: BASELINE configs[4] shape on ONE GPU: 8 sensors x ~123 k points per launch into an
     # 8192x8192 @ 0.05 m map through gem_add_points_multi (launch latency and the fold tail amortised) -----
-    multi = None
-    try:
-        multi = run_multi_sensor(frames, fobjs, npts, peak)
-    except Exception as e:  # never let the secondary measurement break the headline line
-        multi = {"error": repr(e)}
+    extra = {}
+    for name, fn in (("c5_shape_one_gpu", lambda: run_multi_sensor(frames, fobjs, npts, peak)), ("c3", run_c3),
+                     ("reference_gpu_kernels_c2", lambda: time_reference_gpu_kernels(frames[:8], fobjs[:8], 1024, 0.05)),
+                     ("reference_gpu_kernels_c1", lambda: time_reference_gpu_kernels(frames[:4], fobjs[:4], 200, 0.1))):
+        try:
+            extra[name] = fn()
+        except Exception as e:  # never let a secondary measurement break the headline line
+            extra[name] = {"error": repr(e)}
 
     # ---- CPU baseline beside it (bounded sample) ----------------------------------------------------
     threads = best_cpu_threads(frames[: min(F, 16)], L, res)
     nb = int(min(max(K, 5), 40))
     cb_val, cb_ms, cb_n = cpu_baseline(frames[: min(F, 16)], nb, threads, L, res)
     cb1_val, _, _ = cpu_baseline(frames[: min(F, 16)], min(nb, 10), 1, L, res)
+    try:
+        extra["cpu_baseline_c1"] = cpu_baseline_c1(threads)
+    except Exception as e:
+        extra["cpu_baseline_c1"] = {"error": repr(e)}
 
     st = m.stats()
+    extra.update({"host_enqueue_ms_per_step": (host_ms / K) if host_ms is not None else None,
+                  "e2e_frame": e2e_frame, "last_frame_stats": st, "host_cores": os.cpu_count()})
     line = {
         "metric": "Mpoints/s fused into 1024x1024@0.05m grid", "value": value, "unit": "Mpoints/s", "n_gpus": 1,
         "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: HDL-64E-shaped synthetic 10 Hz stream into 1024x1024@0.05m robot-centric map, 1xB200",
+        "config": {"workload": WORKLOAD_C2,
                    "step": ("gem_move + gem_add_points_stream on one frame (device-resident float4 xyzi + uchar4 rgba; "
-                            "consecutive frames software-pipelined)" if stream_mode else
-                            "gem_move + gem_add_points on one frame (device-resident float4 xyzi + uchar4 rgba)"),
+                            "consecutive frames software-pipelined: one CUDA graph {fold of frame i-1 || bin of frame i} per call)"
+                            if stream_mode else "gem_move + gem_add_points on one frame (device-resident float4 xyzi + uchar4 rgba)"),
                    "points_per_frame": float(np.mean(npts)), "distinct_frames": F,
                    "l2": (f"inputs larger than L2: {F} distinct frames = {in_bytes/1e6:.0f} MB cycled" if flush is None
                           else "L2 flushed (256 MB write) between timed steps"),
@@ -433,10 +569,7 @@ def run_single(args):
                          "sample": f"{cb_n} frames of the same stream, oracle process_points+fuse on {threads} threads; "
                                    f"single thread: {cb1_val:.1f} Mpoints/s", "single_thread_value": cb1_val},
         "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
-        "extra": {"c5_shape_one_gpu": multi, "host_enqueue_ms_per_step": (host_ms / K) if host_ms is not None else None,
-                  "frame_ms_full_pipeline": frame_ms,
-                  "frame_pipeline": "move+add+var_update+features+export(9 layers, 37.7 MB D2H into pinned memory)+raytracing, host-synchronous",
-                  "last_frame_stats": st, "host_cores": os.cpu_count()},
+        "extra": extra,
     }
     return line
 

@@ -53,11 +53,17 @@ class GemStats(C.Structure):
                 ("max_points_per_cell", C.c_int)]
 
 
+class GemTiledPeers(C.Structure):
+    _fields_ = [("tiles_r", C.c_int), ("tiles_c", C.c_int), ("my_rank", C.c_int), ("bucket_capacity", C.c_int),
+                ("recv_records", C.c_ulonglong * 64), ("recv_intensity", C.c_ulonglong * 64),
+                ("recv_counts", C.c_ulonglong * 64), ("flags", C.c_ulonglong * 64)]
+
+
 class GemProfile(C.Structure):
     _fields_ = [("launches", C.c_longlong), ("ms", C.c_double * 9), ("count", C.c_longlong * 9)]
 
 
-PROF_CLASSES = ["transform_bin", "alloc_cells", "scatter", "fold", "clear_floor", "features", "raytrace", "other", "route"]
+PROF_CLASSES = ["bin", "fold_long", "unused", "fold", "clear_floor", "features", "raytrace", "other", "route"]
 
 # every symbol include/gem_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -110,6 +116,8 @@ SYMBOLS = {
     "gem_route_points_peer": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame), C.c_int, C.c_int,
                                         C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int, C.c_int]),
     "gem_fuse_records_counted": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
+    "gem_tiled_attach": (C.c_int, [_P, C.POINTER(GemTiledPeers)]),
+    "gem_tiled_step": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),
 }
 
 _lib = None

@@ -985,8 +985,10 @@ constexpr int FOLD_MARKS = 2; // marks per thread and pass: a block's slice is F
 // thread.  fold_blocks blocks fold; blocks beyond them execute `ro` (row / column clears of the NEXT call's Move,
 // pipelined mode only: a cell inside such a region is written with the cleared value by whoever touches it, see cell_end).
 __global__ void __launch_bounds__(ADD_BLOCK, 3)
-k_fold(MapGeom g, MapLayers ml, BinScratch sc, FoldSrc src, const __grid_constant__ RegionOps ro, int n, int fold_blocks, int slice, int do_fuse_i, int do_lowest_i)
+k_fold(MapGeom g, MapLayers ml, BinScratch sc, FoldSrc src, const __grid_constant__ RegionOps ro, int n, int fold_blocks, int slice, int do_fuse_i, int do_lowest_i,
+       const int *n_dev)
 {
+    if (n_dev) n = min(n, *n_dev); // tiled maps: the number of marks is known on the device only (k_bin_peer)
     constexpr int SLICE = FOLD_MARKS * ADD_BLOCK;
     extern __shared__ __align__(16) unsigned char s_dyn[]; // FOLD_SMEM_BYTES: per-warp scratch + the two queues (+ padding, see k_fold_long)
     LargeScratch *s_ws = reinterpret_cast<LargeScratch *>(s_dyn);

@@ -40,7 +40,19 @@ struct PendingFold {
     BinScratch sc{};
     FoldSrc src{};
     MapGeom geom{};   // the geometry the call was binned with (a later Move must not change its lowest indices)
-    int n = 0;
+    int n = 0;        // marks of the call (tiled maps: their capacity; the count is *n_dev)
+    const int *n_dev = nullptr;
+};
+
+struct TiledState { // gem_tiled_attach
+    bool attached = false;
+    int world = 0, my_rank = 0, tiles_r = 0, tiles_c = 0, cap = 0, nblk = 0;
+    PeerBufs pb{};
+    int *d_ticket = nullptr, *d_ntotal = nullptr; // [1], [2] (by call parity)
+    int step = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t long_node = nullptr, fold_node = nullptr, route_node = nullptr, bin_node = nullptr;
 };
 
 struct FrameGraph { // {long lists || the other lists of the previous call || bin of this call} as one three-node CUDA graph
@@ -68,6 +80,7 @@ struct gem_map {
     unsigned call_no = 0;
     BinCounters *ctr_last = nullptr; // counters of the last add call
     PendingFold pend;
+    TiledState tiled;
     // tuning, measured on B200 with scripts/pipe_sweep.sh (profiles/r2_pipe_sweep.txt): GEM_B200_FOLD_BLOCKS, GEM_B200_LONG_BLOCKS,
     // GEM_B200_EXCLUSIVE=1 pads the kernels' shared memory so that k_fold_long's blocks get SMs of their own
     int fold_max_blocks = 148 * 2, long_blocks = LONG_BLOCKS;
@@ -278,8 +291,8 @@ int launch_fold(gem_map *m, cudaStream_t st, const PendingFold &p, const RegionO
     RegionOps none{};
     // the long lists first (their blocks claim whole SMs), then everything else; on one stream the two run back to back
     // (disjoint cells, so the order is free) -- the frame graph of the pipelined mode runs them side by side
-    GEM_LAUNCH_ON(m, st, GEM_PROF_FOLD, k_fold_long<<<long_blocks_for(m, p.n), LONG_BLOCK, m->long_smem, st>>>(p.geom, m->ml, p.sc, p.src, none, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
-    GEM_LAUNCH_ON(m, st, GEM_PROF_FOLD, k_fold<<<fb + region_blocks, ADD_BLOCK, m->fold_smem, st>>>(p.geom, m->ml, p.sc, p.src, ro, p.n, fb, slice, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
+    GEM_LAUNCH_ON(m, st, GEM_PROF_FOLD_LONG, k_fold_long<<<long_blocks_for(m, p.n), LONG_BLOCK, m->long_smem, st>>>(p.geom, m->ml, p.sc, p.src, none, do_fuse ? 1 : 0, do_lowest ? 1 : 0));
+    GEM_LAUNCH_ON(m, st, GEM_PROF_FOLD, k_fold<<<fb + region_blocks, ADD_BLOCK, m->fold_smem, st>>>(p.geom, m->ml, p.sc, p.src, ro, p.n, fb, slice, do_fuse ? 1 : 0, do_lowest ? 1 : 0, p.n_dev));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }
@@ -526,7 +539,7 @@ int enqueue_add(gem_map *m, const BinSource &in, const FoldSrc &fsrc, int n, con
             GEM_CUDA(m, cudaStreamWaitEvent(m->front_stream, m->ev_mark, 0));
             st_bin = m->front_stream;
         }
-        GEM_LAUNCH_ON(m, st_bin, GEM_PROF_TRANSFORM_BIN, bk<<<pb + rb, ADD_BLOCK, m->bin_smem, st_bin>>>(g, ml, f, bin, nn, sc, ro, pb, st, frames));
+        GEM_LAUNCH_ON(m, st_bin, GEM_PROF_BIN, bk<<<pb + rb, ADD_BLOCK, m->bin_smem, st_bin>>>(g, ml, f, bin, nn, sc, ro, pb, st, frames));
         GEM_CUDA(m, cudaGetLastError());
         commit_region_ops(m);
         if (pipelined && m->pipe_mode == 1) GEM_CUDA(m, cudaEventRecord(m->ev_bin[par], st_bin));
@@ -546,12 +559,12 @@ int enqueue_add(gem_map *m, const BinSource &in, const FoldSrc &fsrc, int n, con
         if (m->pipe_mode == 2) {
             int pbk = pb, one = 1, fbk = fb;
             void *bin_args[] = {&g, &ml, &f, &bin, &nn, &sc, &none, &pbk, &st, (void *)&frames};
-            void *fold_args[] = {&prev.geom, &ml, &prev.sc, &prev.src, &ro, &prev.n, &fbk, &slice, &one, &one};
+            void *fold_args[] = {&prev.geom, &ml, &prev.sc, &prev.src, &ro, &prev.n, &fbk, &slice, &one, &one, (void *)&prev.n_dev};
             void *long_args[] = {&prev.geom, &ml, &prev.sc, &prev.src, &none, &one, &one};
             if ((rc = launch_frame_graph(m, bk, bin_args, pb, fold_args, fb + rb, long_args, long_blocks_for(m, prev.n)))) return rc;
         } else {
             GEM_CUDA(m, cudaStreamWaitEvent(m->front_stream, m->ev_fold[par], 0)); // the fold that last used this parity's scratch
-            GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_TRANSFORM_BIN, bk<<<pb, ADD_BLOCK, m->bin_smem, m->front_stream>>>(g, ml, f, bin, nn, sc, none, pb, st, frames));
+            GEM_LAUNCH_ON(m, m->front_stream, GEM_PROF_BIN, bk<<<pb, ADD_BLOCK, m->bin_smem, m->front_stream>>>(g, ml, f, bin, nn, sc, none, pb, st, frames));
             GEM_CUDA(m, cudaEventRecord(m->ev_bin[par], m->front_stream));
             GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_bin[prev.sc.par], 0));
             if ((rc = launch_fold(m, m->stream, prev, ro, rb, true, true))) return rc;
@@ -734,6 +747,8 @@ int gem_destroy(gem_map *m)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
             if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
         }
+        if (m->tiled.exec) cudaGraphExecDestroy(m->tiled.exec);
+        if (m->tiled.graph) cudaGraphDestroy(m->tiled.graph);
         for (auto &sp : m->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
         for (cudaEvent_t e : m->free_events) cudaEventDestroy(e);
         for (void *p : m->allocs) cudaFree(p);
@@ -1600,6 +1615,127 @@ int gem_route_points_peer(gem_map *m, const void *xyzi, const void *rgba, int n,
                                        m->route_sc, nullptr, m->d_owner_cnt, bucket_stride, &pt, my_rank);
     m->launches += 3;
     if (e != cudaSuccess) return fail(m, GEM_ERR_CUDA, std::string("gem_route_points_peer: ") + cudaGetErrorString(e));
+    return GEM_OK;
+}
+
+// ---- tiled maps, peer path (gem_route.cuh "Peer path, round 2") --------------------------------------------------------
+int gem_tiled_attach(gem_map *m, const gem_tiled_peers *p)
+{
+    if (!m || !p) return fail(m, GEM_ERR_INVALID, "gem_tiled_attach: null argument");
+    Lock lk(m->mu);
+    SetDev sd(m->dev);
+    if (!m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_tiled_attach: handle is not tiled");
+    const int world = p->tiles_r * p->tiles_c;
+    if (world < 1 || world > ROUTE_MAX_OWNERS || p->my_rank < 0 || p->my_rank >= world || p->bucket_capacity < 1)
+        return fail(m, GEM_ERR_INVALID, "gem_tiled_attach: bad geometry");
+    const int nblk = (p->bucket_capacity + ROUTE_BLOCK - 1) / ROUTE_BLOCK, cap = nblk * ROUTE_BLOCK;
+    if ((long long)world * cap > m->P) return fail(m, GEM_ERR_INVALID, "gem_tiled_attach: world * bucket_capacity exceeds max_points");
+    int rc = drain(m);
+    if (rc) return rc;
+    TiledState &ts = m->tiled;
+    ts.world = world; ts.my_rank = p->my_rank; ts.tiles_r = p->tiles_r; ts.tiles_c = p->tiles_c; ts.cap = cap; ts.nblk = nblk;
+    for (int o = 0; o < world; o++) {
+        ts.pb.rec[o] = p->recv_records[o]; ts.pb.inten[o] = p->recv_intensity[o];
+        ts.pb.cnt[o] = p->recv_counts[o]; ts.pb.flag[o] = p->flags[o];
+    }
+    if (!ts.d_ticket && (rc = dev_alloc(m, &ts.d_ticket, 4))) return rc;
+    ts.d_ntotal = ts.d_ticket + 1;
+    GEM_CUDA(m, cudaMemsetAsync(ts.d_ticket, 0, 4 * sizeof(int), m->stream));
+    ts.step = 0;
+    ts.attached = true;
+    return GEM_OK;
+}
+
+// One step of a tiled map: route this rank's cloud to the owning tiles (peer stores), bin what the peers delivered,
+// fold.  Pipelined like gem_add_points_stream: the step issues ONE graph {fold_long, fold of the previous step ||
+// route -> bin of this step}; the fold of the last step is issued by whatever reads the map next (gem_flush).
+// Every rank must make the same sequence of gem_tiled_step calls (a step waits for every peer's flag of that step).
+int gem_tiled_step(gem_map *m, const void *xyzi, const void *rgba, int n, const gem_frame *frame)
+{
+    if (!m || !frame || n < 0 || (n > 0 && !xyzi)) return fail(m, GEM_ERR_INVALID, "gem_tiled_step: bad argument");
+    Lock lk(m->mu);
+    SetDev sd(m->dev);
+    TiledState &ts = m->tiled;
+    if (!ts.attached) return fail(m, GEM_ERR_INVALID, "gem_tiled_step: gem_tiled_attach first");
+    if (n > ts.cap) return fail(m, GEM_ERR_INVALID, "gem_tiled_step: cloud larger than bucket_capacity");
+    int rc;
+    const bool serial = m->profiling || m->pipe_mode == 0;
+    if (serial && (rc = drain(m))) return rc;
+    if (!m->pending.empty()) { // tiled maps do not scroll: only the first-fuse floor can be pending
+        if ((rc = drain(m)) || (rc = flush_all_pending(m))) return rc;
+    }
+    ts.step++;
+    const int step = ts.step, buf = step % 3, world = ts.world, nsub = world * ts.nblk;
+    const int par = (int)(m->call_no & 1u), c = (int)(m->call_no % 3u);
+    BinScratch sc = m->bs[par];
+    sc.ctr = m->ctr[c];
+    sc.ctr_next = m->ctr[(c + 1) % 3];
+    sc.par = par;
+    sc.stamps = nullptr;
+    MapGeom gg = m->geom, gl = m->geom;
+    gg.tiled = 0; // routing works on global geographic indices
+    FrameParams fp = make_frame(frame);
+    const int tile_h = (m->L + ts.tiles_r - 1) / ts.tiles_r, tile_w = (m->L + ts.tiles_c - 1) / ts.tiles_c;
+    const float4 *px = (const float4 *)xyzi;
+    const uchar4 *pr = (const uchar4 *)rgba;
+    int nn = n, tiles_c = ts.tiles_c, my_rank = ts.my_rank, nblk = ts.nblk, cap = ts.cap, bufv = buf, stepv = step, worldv = world, nsubv = nsub;
+    int *ticket = ts.d_ticket, *ntotal = ts.d_ntotal + par;
+    PeerBufs pb = ts.pb;
+    const uint4 *my_rec = (const uint4 *)pb.rec[my_rank] + (size_t)buf * world * cap;
+    const float *my_int = (const float *)pb.inten[my_rank] + (size_t)buf * world * cap;
+    const int *my_cnt = (const int *)pb.cnt[my_rank] + (size_t)buf * nsub;
+    const int *my_flags = (const int *)pb.flag[my_rank];
+    MapLayers ml = m->ml;
+    int th = tile_h, tw = tile_w;
+    void *route_args[] = {&gg, &fp, &px, &pr, &nn, &th, &tw, &tiles_c, &worldv, &my_rank, &nblk, &cap, &bufv, &stepv, &pb, &ticket};
+    void *bin_args[] = {&gl, &ml, &sc, &my_rec, &my_int, &my_cnt, &nsubv, &my_flags, &worldv, &stepv, &ntotal};
+    PendingFold cur;
+    cur.active = true; cur.sc = sc; cur.geom = m->geom; cur.n = world * cap; cur.n_dev = ntotal;
+    cur.src = FoldSrc{(const char *)my_int, 4};
+    if (serial || !m->pend.active || m->pipe_mode != 2) {
+        if ((rc = drain(m))) return rc;
+        GEM_LAUNCH(m, GEM_PROF_ROUTE, k_route_peer<<<nblk, ROUTE_BLOCK, 0, m->stream>>>(gg, fp, px, pr, nn, th, tw, tiles_c, worldv, my_rank, nblk, cap, bufv, stepv, pb, ticket));
+        GEM_LAUNCH(m, GEM_PROF_BIN, k_bin_peer<<<nsub, ROUTE_BLOCK, 0, m->stream>>>(gl, ml, sc, my_rec, my_int, my_cnt, nsubv, my_flags, worldv, stepv, ntotal));
+        GEM_CUDA(m, cudaGetLastError());
+        if (serial) {
+            RegionOps none{};
+            if ((rc = launch_fold(m, m->stream, cur, none, 0, true, true))) return rc;
+        } else {
+            m->pend = cur;
+        }
+    } else {
+        PendingFold prev = m->pend;
+        const int fb = fold_blocks_for(m, prev.n);
+        int slice = fold_slice(prev.n, fb), fbk = fb, one = 1;
+        RegionOps none{};
+        void *fold_args[] = {&prev.geom, &ml, &prev.sc, &prev.src, &none, &prev.n, &fbk, &slice, &one, &one, (void *)&prev.n_dev};
+        void *long_args[] = {&prev.geom, &ml, &prev.sc, &prev.src, &none, &one, &one};
+        cudaKernelNodeParams kl{}, kf{}, kr{}, kb{};
+        kl.func = (void *)k_fold_long; kl.gridDim = dim3((unsigned)long_blocks_for(m, prev.n / world)); kl.blockDim = dim3(LONG_BLOCK); kl.sharedMemBytes = (unsigned)m->long_smem; kl.kernelParams = long_args;
+        kf.func = (void *)k_fold; kf.gridDim = dim3((unsigned)fb); kf.blockDim = dim3(ADD_BLOCK); kf.sharedMemBytes = (unsigned)m->fold_smem; kf.kernelParams = fold_args;
+        kr.func = (void *)k_route_peer; kr.gridDim = dim3((unsigned)nblk); kr.blockDim = dim3(ROUTE_BLOCK); kr.sharedMemBytes = 0; kr.kernelParams = route_args;
+        kb.func = (void *)k_bin_peer; kb.gridDim = dim3((unsigned)nsub); kb.blockDim = dim3(ROUTE_BLOCK); kb.sharedMemBytes = 0; kb.kernelParams = bin_args;
+        if (!ts.exec) {
+            GEM_CUDA(m, cudaGraphCreate(&ts.graph, 0));
+            GEM_CUDA(m, cudaGraphAddKernelNode(&ts.long_node, ts.graph, nullptr, 0, &kl));
+            GEM_CUDA(m, cudaGraphAddKernelNode(&ts.route_node, ts.graph, nullptr, 0, &kr));
+            GEM_CUDA(m, cudaGraphAddKernelNode(&ts.fold_node, ts.graph, nullptr, 0, &kf));
+            GEM_CUDA(m, cudaGraphAddKernelNode(&ts.bin_node, ts.graph, &ts.route_node, 1, &kb));
+            GEM_CUDA(m, cudaGraphInstantiate(&ts.exec, ts.graph, 0));
+        } else {
+            GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.long_node, &kl));
+            GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.route_node, &kr));
+            GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.fold_node, &kf));
+            GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.bin_node, &kb));
+        }
+        GEM_CUDA(m, cudaGraphLaunch(ts.exec, m->stream));
+        m->launches += 4;
+        m->pend = cur;
+    }
+    m->ctr_last = sc.ctr;
+    m->call_no++;
+    memset(&m->stats, 0, sizeof m->stats);
+    m->stats.points_in = n;
     return GEM_OK;
 }
 

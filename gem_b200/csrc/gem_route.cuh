@@ -187,4 +187,159 @@ inline cudaError_t route_points(cudaStream_t st, const MapGeom &g, const FramePa
     return cudaGetLastError();
 }
 
+// =========================================================================================
+// Peer path, round 2: route + exchange in ONE kernel, no collective library, no barrier kernel.
+//
+//   k_route_peer   (source rank r)  1 thread/point: transform, owner tile, stable position inside the block's
+//                  sub-bucket, record stored straight into the owner's receive buffer over NVLink; every block also
+//                  stores its per-owner count; the last block to finish raises this rank's flag on every peer
+//   k_bin_peer     (owner rank)     1 block per (source rank, source block) sub-bucket of 256 slots: waits for all
+//                  peers' flags of this step, skips empty sub-buckets, bins the received records like k_bin does
+//
+// Determinism: rank r's block b owns slots [(r * nblk + b) * 256, +256) of every owner's buffer, filled in source
+// order without a cross-block scan.  The slot index is monotone in (source rank, source point index), and it is the
+// slot index that the fold sorts a cell's records by -- so the tiled map equals the single-GPU map of the rank-by-rank
+// concatenated clouds bit for bit, although the buffer has holes.  The work list (marks) is dense: a sub-bucket's marks
+// start at the sum of the counts in front of it.
+// Receive buffers are triple-buffered by step: the fold of step i-1 (issued with step i) still reads intensities from
+// buffer (i-1) % 3 while the peers of step i write buffer i % 3; buffer (i+2) % 3 = (i-1) % 3 is written in step i+2,
+// which no peer can reach before this rank has raised its flag of step i+1, i.e. after its graph of step i (with that
+// fold) has completed.
+// =========================================================================================
+struct PeerBufs { // device addresses valid on THIS device (own memory or peer mappings), per rank
+    unsigned long long rec[ROUTE_MAX_OWNERS];   // uint4 [3][world * cap]  {gkey, h, var, rgb}
+    unsigned long long inten[ROUTE_MAX_OWNERS]; // float [3][world * cap]
+    unsigned long long cnt[ROUTE_MAX_OWNERS];   // int   [3][world * nblk]
+    unsigned long long flag[ROUTE_MAX_OWNERS];  // int   [world]: flag[o][r] = last step rank r has delivered to rank o
+};
+
+__global__ void __launch_bounds__(ROUTE_BLOCK)
+k_route_peer(MapGeom g, FrameParams f, const float4 *xyzi, const uchar4 *rgba, int n, int tile_h, int tile_w, int tiles_c, int world,
+             int my_rank, int nblk, int cap, int buf, int step, const __grid_constant__ PeerBufs pb, int *ticket)
+{
+    __shared__ int s_wcnt[ROUTE_BLOCK / 32][ROUTE_MAX_OWNERS];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const int w = threadIdx.x >> 5;
+    for (int o = (int)lane; o < world; o += 32) s_wcnt[w][o] = 0;
+    __syncwarp();
+    int owner = -1, gkey = -1;
+    float h = 0.0f, hv = 0.0f, inten = 0.0f;
+    uint32_t rgb = 0u;
+    if (i < n) {
+        const float4 p = ld_stream_f4(xyzi + i);
+        const PtRes r = transform_point(g, f, p.x, p.y, p.z);
+        if (r.ingrid) {
+            owner = (r.gx / tile_h) * tiles_c + (r.gy / tile_w);
+            gkey = r.gx * g.L + r.gy;
+            h = r.h; hv = r.hv; inten = p.w;
+            if (rgba) { const uchar4 c = rgba[i]; rgb = pack_rgb(c.x, c.y, c.z); }
+        }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, owner);
+    const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (owner >= 0 && rank_in_warp == 0) s_wcnt[w][owner] = __popc(peers);
+    __syncthreads();
+    const size_t sub = (size_t)my_rank * nblk + blockIdx.x; // this block's sub-bucket in every owner's buffer
+    if (owner >= 0) {
+        int before = 0;
+        for (int ww = 0; ww < w; ww++) before += s_wcnt[ww][owner];
+        const size_t slot = (size_t)buf * world * cap + sub * ROUTE_BLOCK + before + rank_in_warp;
+        reinterpret_cast<uint4 *>(pb.rec[owner])[slot] = make_uint4((uint32_t)gkey, __float_as_uint(h), __float_as_uint(hv), rgb); // NVLink
+        reinterpret_cast<float *>(pb.inten[owner])[slot] = inten;
+    }
+    if ((int)threadIdx.x < world) { // this block's count for every owner (zero included: the owner must not read a stale one)
+        int tot = 0;
+        for (int ww = 0; ww < ROUTE_BLOCK / 32; ww++) tot += s_wcnt[ww][threadIdx.x];
+        reinterpret_cast<int *>(pb.cnt[threadIdx.x])[(size_t)buf * world * nblk + sub] = tot;
+    }
+    __threadfence_system(); // this thread's peer stores are ordered before the flag below
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        if (t == (int)gridDim.x - 1) { // last block of this rank: everything is on its way -> raise the flag on every peer
+            *ticket = 0;
+            __threadfence_system();
+            for (int o = 0; o < world; o++)
+                asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(reinterpret_cast<int *>(pb.flag[o]) + my_rank), "r"(step) : "memory");
+        }
+    }
+}
+
+// one point of the bin kernel, U = 1 (see bin_points for the argument why the waits cannot deadlock)
+__device__ __forceinline__ void bin_one(Cell *cells, const BinScratch &sc, int key, int geo, uint4 rec, int i_rec, int i_mark)
+{
+    const int par = sc.par;
+    const int rank = (key >= 0) ? atomicAdd(&cells[key].bin[par].x, 1) : -1;
+    int kind = MARK_NONE, z = 0, lvl = 0, myp = 0;
+    if (rank == 0) { kind = MARK_FIRST; z = geo; }
+    else if (rank == CHUNK0) { kind = MARK_LARGE; z = i_rec; st_relaxed(&cells[key].bin[par].y, i_rec + 1); }
+    else if (rank >= FOLD_LONG_FROM) {
+        const int j = level_of(rank);
+        if (rank == level_base(j)) { lvl = j; myp = 1 + atomicAdd(&sc.ctr->pool, level_cap(j) + 1); }
+    }
+    sc.mark[i_mark] = make_int4(key, kind, z, 0);
+    if (rank < 0) return;
+    uint4 *dst;
+    if (rank < CHUNK0) {
+        dst = sc.chunk0 + (size_t)CHUNK0 * key + rank;
+    } else {
+        const int i8 = (rank == CHUNK0) ? i_rec : spin_nonzero(&cells[key].bin[par].y) - 1;
+        uint4 *q = sc.pool1 + (size_t)CHUNK1_SLOTS * i8;
+        const int j = level_of(rank);
+        if (lvl >= 2) { // publish the chunk this point allocated in the header of the level below
+            uint4 *below = q;
+            for (int k = 2; k < lvl; k++) below = sc.pool + spin_next(below);
+            if (lvl == 2) sc.tlong[atomicAdd(&sc.ctr->nlong, 1)] = make_int4(key, MARK_LONG, i8, myp);
+            publish_next(below, myp);
+        }
+        for (int k = 2; k <= j; k++) q = sc.pool + ((lvl == k) ? myp : spin_next(q));
+        dst = q + 1 + (rank - level_base(j));
+    }
+    *dst = rec;
+}
+
+__global__ void __launch_bounds__(ROUTE_BLOCK)
+k_bin_peer(MapGeom g, MapLayers ml, BinScratch sc, const uint4 *rec, const float *inten, const int *cnt, int nsub, const int *flags,
+           int world, int step, int *n_total)
+{
+    __shared__ int s_red[ROUTE_BLOCK / 32];
+    __shared__ int s_base;
+    const int sb = blockIdx.x;
+    if (sb == 0) zero_next_counters(sc, threadIdx.x);
+    if (threadIdx.x == 0) { // all peers have delivered this step (their records, counts and everything before the flag)
+        for (int r = 0; r < world; r++) {
+            int v;
+            do {
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+                if (v < step) __nanosleep(100);
+            } while (v < step);
+        }
+    }
+    __syncthreads();
+    const int c = cnt[sb];
+    const bool last = sb == nsub - 1;
+    if (c == 0 && !last) return;
+    int part = 0; // dense start of this sub-bucket's marks = sum of the counts in front of it
+    for (int j = threadIdx.x; j < sb; j += ROUTE_BLOCK) part += cnt[j];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if ((threadIdx.x & 31u) == 0u) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int ww = 0; ww < ROUTE_BLOCK / 32; ww++) b += s_red[ww];
+        s_base = b;
+        if (last) *n_total = b + c;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= c) return;
+    const int slot = sb * ROUTE_BLOCK + threadIdx.x; // monotone in (source rank, source point index): the fold's sort key
+    const uint4 r = rec[slot];
+    const int gkey = (int)r.x;
+    const int gx = gkey / g.L, gy = gkey - gx * g.L;
+    const int key = local_key(g, gx, gy);
+    bin_one(ml.cell, sc, key, g.tiled ? key : gkey, make_uint4((uint32_t)slot, r.y, r.z, with_colour_flag(r.w, inten[slot])), slot, s_base + threadIdx.x);
+}
+
 } // namespace gem

@@ -437,5 +437,20 @@ class ElevationMap:
         rc = self._lib.gem_fuse_records_counted(self._h, _ptr(rec), _ptr(src_counts), int(n_sources), int(bucket_stride))
         check(rc, self._h, "gem_fuse_records_counted")
 
+    def tiled_attach(self, tiles_r, tiles_c, my_rank, bucket_capacity, recv_records, recv_intensity, recv_counts, flags):
+        """gem_tiled_attach: lists of device addresses (ints), one per rank, of the four peer-accessible buffers"""
+        p = _lib.GemTiledPeers()
+        p.tiles_r, p.tiles_c, p.my_rank, p.bucket_capacity = int(tiles_r), int(tiles_c), int(my_rank), int(bucket_capacity)
+        for o in range(len(recv_records)):
+            p.recv_records[o], p.recv_intensity[o] = int(recv_records[o]), int(recv_intensity[o])
+            p.recv_counts[o], p.flags[o] = int(recv_counts[o]), int(flags[o])
+        check(self._lib.gem_tiled_attach(self._h, C.byref(p)), self._h, "gem_tiled_attach")
+
+    def tiled_step(self, xyzi, rgba, frame: GemFrame, n: int | None = None):
+        n = int(xyzi.shape[0]) if n is None else int(n)
+        rc = self._lib.gem_tiled_step(self._h, _ptr(xyzi), _ptr(rgba), n, C.byref(frame))
+        if rc:
+            check(rc, self._h, "gem_tiled_step")
+
     def fuse_records(self, rec, n: int):
         check(self._lib.gem_fuse_records(self._h, _ptr(rec), int(n)), self._h, "gem_fuse_records")

@@ -115,10 +115,10 @@ class TiledElevationMap:
     bucket_capacity > 0 selects the padded exchange: every (source, destination) bucket has that
     fixed capacity (>= the largest cloud a rank adds per step), one fixed-size all-to-all per
     step and no host-side split sizes; 0 selects the packed exchange (counts all-to-all + D2H).
-    peer=True (needs bucket_capacity) takes NCCL off the data path altogether: the routing kernel
-    stores every record straight into the owning rank's receive buffer over NVLink (torch symmetric
-    memory supplies the peer mappings) and one signal-pad barrier per step orders route -> fold;
-    receive buffers are double-buffered by step parity."""
+    peer=True (needs bucket_capacity) takes NCCL off the data path altogether: gem_tiled_step's routing
+    kernel stores every record straight into the owning rank's receive buffer over NVLink and raises a
+    flag there; the owner's bin kernel waits for the flags of the step.  torch symmetric memory only
+    ALLOCATES the peer-mapped buffers (set-up); no torch / NCCL call is on the per-step path."""
 
     def __init__(self, length: int, resolution: float, max_points: int = 1 << 20, compat_box_filter: bool = False,
                  bucket_capacity: int = 0, peer: bool = False):
@@ -151,17 +151,22 @@ class TiledElevationMap:
         self.step = 0
         if self.peer:
             import torch.distributed._symmetric_memory as symm_mem
+            nblk = (self.cap + 255) // 256
+            self.cap = nblk * 256
+            grp = dist.group.WORLD.group_name
             with torch.cuda.stream(self.stream):
-                self.p_recv = symm_mem.empty((2, self.world * self.cap, REC_WORDS), dtype=torch.int32, device=self.dev)
-                self.p_cnt = symm_mem.empty((2, 64), dtype=torch.int32, device=self.dev)
+                self.p_rec = symm_mem.empty((3, self.world * self.cap, 4), dtype=torch.int32, device=self.dev)
+                self.p_int = symm_mem.empty((3, self.world * self.cap), dtype=torch.float32, device=self.dev)
+                self.p_cnt = symm_mem.empty((3, self.world * nblk), dtype=torch.int32, device=self.dev)
+                self.p_flag = symm_mem.empty((64,), dtype=torch.int32, device=self.dev)
                 self.p_cnt.zero_()
-                self.h_recv = symm_mem.rendezvous(self.p_recv, dist.group.WORLD.group_name)
-                self.h_cnt = symm_mem.rendezvous(self.p_cnt, dist.group.WORLD.group_name)
-                self.h_recv.barrier(channel=0)
+                self.p_flag.zero_()
+                hs = [symm_mem.rendezvous(t, grp) for t in (self.p_rec, self.p_int, self.p_cnt, self.p_flag)]
+                hs[0].barrier(channel=0)            # set-up only: every rank's flags are zero before anyone steps
             self.stream.synchronize()
-            rec_bytes = self.world * self.cap * REC_WORDS * 4
-            self._peer_recv = [[int(p) + par * rec_bytes for p in self.h_recv.buffer_ptrs] for par in (0, 1)]
-            self._peer_cnt = [[int(p) + par * 64 * 4 for p in self.h_cnt.buffer_ptrs] for par in (0, 1)]
+            self._handles = hs
+            ptrs = [[int(p) for p in h.buffer_ptrs] for h in hs]
+            self.map.tiled_attach(self.tiles_r, self.tiles_c, self.rank, self.cap, ptrs[0], ptrs[1], ptrs[2], ptrs[3])
 
     def add(self, xyzi, rgba, frame):
         """route this rank's cloud, exchange, fold the received records into the own tile"""
@@ -171,13 +176,8 @@ class TiledElevationMap:
             if self.peer:
                 if int(xyzi.shape[0]) > self.cap:
                     raise ValueError("cloud larger than bucket_capacity")
-                par = self.step & 1
                 self.step += 1
-                # one kernel transforms, buckets and stores into the owners' memory over NVLink
-                self.map.route_points_peer(xyzi, rgba, frame, self.tiles_r, self.tiles_c, self._peer_recv[par],
-                                           self._peer_cnt[par], self.rank, self.cap)
-                self.h_recv.barrier(channel=0)          # device-side, on this stream: all peers' stores landed
-                self.map.fuse_records_counted(self.p_recv[par], self.p_cnt[par], self.world, self.cap)
+                self.map.tiled_step(xyzi, rgba, frame)   # route + exchange + bin (+ the previous step's fold): one graph launch
                 self.last_recv = self.world * self.cap
                 return None, None
             if self.cap:
@@ -242,6 +242,81 @@ class TiledElevationMap:
         return self.map.get_layer(name)
 
 
+def parity_check(mode: str = "peer", steps: int = 3, L_per_rank: int = 512, res: float = 0.1, with_cleanup: bool = True):
+    """N ranks build a tiled map and compare it with the untiled map that rank 0 computes alone on the same clouds
+    (gem_add_points_multi of the rank-by-rank concatenated clouds), bit for bit, layer by layer.  Collective: every
+    rank of the default process group must call it.  Returns {"status", "mismatching_cells", "cells_checked",
+    "valid_cells", "ranks", "mode"} on rank 0 (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    import gem_b200
+    from . import synth
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    L = L_per_rank * world
+    scene = synth.make_scene()
+
+    def cloud(r, s):
+        fr = synth.hdl64_frame(10 * r + s, scene=scene)
+        ox, oy = sensor_offset(r, world)
+        fr["T"] = fr["T"].copy()
+        fr["T"][:2, 3] = (ox * 0.5 + s, oy * 0.5)
+        return fr, gem_b200.make_frame(fr["T"], gem_b200.LaserSensorProcessor())
+
+    tm = TiledElevationMap(L, res, max_points=1 << 20, bucket_capacity=0 if mode == "packed" else (1 << 17) + 4096,
+                           peer=(mode == "peer"))
+    keep = []
+    for s in range(steps):
+        fr, f = cloud(rank, s)
+        x, c = torch.from_numpy(fr["xyzi"]).to(dev), torch.from_numpy(fr["rgba"]).to(dev)
+        keep.append((x, c))      # the pipelined step reads its inputs again when the NEXT step (or the drain) folds
+        tm.add(x, c, f)
+    pos = np.array([0.0, 0.0, 1.8], np.float32)
+    tm.map.move(pos)
+    names = ["elevation", "variance", "intensity", "color_r", "lowest"]
+    if with_cleanup:
+        tm.compute_features()      # halo all-gather + 5x5 PCA on the padded tile
+        tm.clean()                 # replicated lowest + ray clean-up of the own tile
+        names = ["elevation", "variance", "intensity", "color_r", "traver", "rough", "slope", "lowest"]
+    tm.map.sync()
+    torch.cuda.synchronize()
+    bad = checked = valid = 0
+    full = None
+    if rank == 0:
+        single = gem_b200.ElevationMap(L, res, compat_box_filter=False)
+        single.move(pos)
+        for s in range(steps):          # per step ONE multi-sensor frame: the ranks' clouds in rank order
+            cl = [cloud(r, s) for r in range(world)]
+            xa = torch.cat([torch.from_numpy(c[0]["xyzi"]) for c in cl]).to(dev)
+            ca = torch.cat([torch.from_numpy(c[0]["rgba"]) for c in cl]).to(dev)
+            offs = np.concatenate([[0], np.cumsum([c[0]["xyzi"].shape[0] for c in cl])])
+            single.add_multi(xa, ca, offs, [c[1] for c in cl])
+            single.sync()
+        if with_cleanup:
+            single.compute_features()
+            single.raytracing()
+        full = {n: single.get_layer(n) for n in names}
+        single.close()
+    for name in names:
+        mine = torch.from_numpy(tm.get_layer(name).astype(np.float32).copy()).to(dev)
+        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, gathered, dst=0)
+        if rank == 0:
+            for r in range(world):
+                r0, nr, c0, nc = tile_of_rank(r, world, L)
+                a = gathered[r].cpu().numpy()
+                b = full[name][r0:r0 + nr, c0:c0 + nc].astype(np.float32)
+                bad += int((a.view(np.uint32) != b.view(np.uint32)).sum())
+                checked += a.size
+    dist.barrier()
+    tm.map.close()
+    if rank != 0:
+        return None
+    valid = int((full["elevation"] != -10).sum())
+    return {"status": "ok" if bad == 0 and valid > 10000 else "FAILED", "mismatching_cells": bad, "cells_checked": checked,
+            "valid_cells": valid, "ranks": world, "mode": mode, "layers": names, "steps": steps, "grid": f"{L}x{L}@{res}"}
+
+
 # ------------------------------------------------------------------------------------------
 # multi-GPU leg of bench.py
 # ------------------------------------------------------------------------------------------
@@ -298,6 +373,14 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
         tm = TiledElevationMap(L, res, max_points=max(1 << 21, world * cap), bucket_capacity=cap)
     cap = tm.cap
     stream = tm.stream
+    # driver-visible multi-rank parity: the same code path that is timed below, at a size the
+    # single-GPU twin computes in seconds, compared bit for bit on rank 0
+    parity = None
+    if os.environ.get("GEM_B200_BENCH_PARITY", "1") == "1":
+        try:
+            parity = parity_check(mode="peer" if tm.peer else "padded", with_cleanup=False)
+        except Exception as e:
+            parity = {"status": "ERROR", "error": repr(e)}
 
     def step(s):
         k = pingpong(s, F)
@@ -318,6 +401,7 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
     e0.record(stream)
     for s in range(K):
         pts += step(s0 + s)
+    tm.map.flush()        # the last step's fold (deferred by the step pipeline)
     e1.record(stream)
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -332,8 +416,8 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
     # ---- e2e: pinned host clouds, H2D inside the timed region, per-step D2H of the routed counts ----
     xyzi_h = [torch.from_numpy(fr["xyzi"]).pin_memory() for fr in frames]
     rgba_h = [torch.from_numpy(fr["rgba"]).pin_memory() for fr in frames]
-    xs = torch.empty((cap, 4), dtype=torch.float32, device=dev)
-    rs = torch.empty((cap, 4), dtype=torch.uint8, device=dev)
+    xs = [torch.empty((cap, 4), dtype=torch.float32, device=dev) for _ in range(3)]   # three staging sets: the fold of
+    rs = [torch.empty((cap, 4), dtype=torch.uint8, device=dev) for _ in range(3)]     # step i reads step i's input in step i+1
     Ke = min(K, 200)
     dist.barrier()
     torch.cuda.synchronize()
@@ -342,12 +426,13 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
     for s in range(Ke):
         k = pingpong(s0 + K + s, F)
         with torch.cuda.stream(stream):
-            xs[: npts[k]].copy_(xyzi_h[k], non_blocking=True)
-            rs[: npts[k]].copy_(rgba_h[k], non_blocking=True)
-        tm.add(xs[: npts[k]], rs[: npts[k]], fobjs[k])
+            xs[k % 3][: npts[k]].copy_(xyzi_h[k], non_blocking=True)
+            rs[k % 3][: npts[k]].copy_(rgba_h[k], non_blocking=True)
+        tm.add(xs[k % 3][: npts[k]], rs[k % 3][: npts[k]], fobjs[k])
         with torch.cuda.stream(stream):
-            _ = tm.counts.cpu()          # D2H of the per-owner counts = the step's host-visible result
+            _ = tm.counts.cpu()          # a small D2H per step = the step's host-visible result
         epts += npts[k]
+    tm.map.flush()
     e1.record(stream)
     torch.cuda.synchronize()
     ems = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -367,12 +452,13 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
             "metric": "Mpoints/s fused into tiled grid", "value": value, "unit": "Mpoints/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{world} HDL-64E-shaped sensors (one per GPU) into one {L}x{L}@0.05m global map "
-                                   f"tiled {tm.tiles_r}x{tm.tiles_c} across {world}xB200, NCCL all-to-all point routing "
-                                   "(configs[3]/[4] shape)",
+            "config": {"workload": (f"{world} HDL-64E-shaped sensors (one per GPU) into one {L}x{L}@0.05m global map tiled across "
+                                    f"{world}xB200, points routed to the owning tile over NVLink (configs[3]/[4] shape)"),
+                       "tiles": f"{tm.tiles_r}x{tm.tiles_c}",
                        "points_per_frame_per_gpu": float(np.mean(npts)), "distinct_frames": F,
-                       "exchange": ("peer-memory routing kernel: records stored directly into the owning GPU over NVLink "
-                                    "(symmetric memory), one signal-pad barrier per step" if tm.peer else
+                       "exchange": ("gem_tiled_step: one routing kernel stores the records straight into the owning GPU over NVLink and "
+                                    "raises a flag there; the owner's bin kernel waits for the step's flags; steps pipelined "
+                                    "(one 4-node CUDA graph per step); no NCCL / torch call on the per-step path" if tm.peer else
                                     f"one fixed-size NCCL all-to-all per step, {cap} x 20 B records per (src,dst) pair"),
                        "l2": f"inputs larger than L2 per GPU: {F} frames cycled", "box_filter": "off"},
             "roofline": {"bound": "hbm", "achieved": algo / (ms_total / K * 1e-3) / 1e9 / world, "peak": peak,
@@ -381,6 +467,7 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
             "cpu_baseline": None,
             "e2e": e2e,
             "clocks": clocks, "gpu_launches": int(tot[1].item()),
+            "tiled_parity": parity,
             "extra": {"rank0_last_step_stats": last_stats},
         }
     dist.barrier()

@@ -260,9 +260,10 @@ int gem_get_stats(gem_map *m, gem_stats *out);
  * (bin, then fold, nothing overlapped), so the per-kernel durations are uncontended.
  * gem_profile_read synchronises the stream. */
 enum {
-    GEM_PROF_TRANSFORM_BIN = 0, /* k_bin: transform + bin + in-kernel slot allocation + record store */
-    GEM_PROF_ALLOC = 1, GEM_PROF_SCATTER = 2, /* unused since the round-2 add path (kept for ABI stability) */
-    GEM_PROF_FOLD = 3,
+    GEM_PROF_BIN = 0,       /* k_bin: transform + bin + record store */
+    GEM_PROF_FOLD_LONG = 1, /* k_fold_long: the cells with more than 40 records of the call */
+    GEM_PROF_UNUSED = 2,
+    GEM_PROF_FOLD = 3,      /* k_fold: all other cells */
     GEM_PROF_CLEAR = 4, GEM_PROF_FEATURES = 5, GEM_PROF_RAYTRACE = 6, GEM_PROF_OTHER = 7,
     GEM_PROF_ROUTE = 8, /* tiled maps: the routing kernel */
     GEM_PROF_CLASSES = 9
@@ -325,6 +326,27 @@ int gem_route_points_peer(gem_map *m, const void *xyzi_device, const void *rgba_
  * src_counts_device[s] */
 int gem_fuse_records_counted(gem_map *m, const void *rec_device, const int *src_counts_device, int n_sources,
                              int bucket_stride);
+
+/* ---- tiled maps, peer path: one kernel routes AND exchanges (no collective library, no barrier kernel) ----------
+ * The caller allocates, on every rank, four peer-accessible buffers (e.g. CUDA IPC / torch symmetric memory; the
+ * library does no inter-process plumbing) and passes the addresses under which THIS device sees every rank's copy:
+ *   recv_records   uint4 [3][world * cap]   {global geographic key, height, variance, rgb}
+ *   recv_intensity float [3][world * cap]
+ *   recv_counts    int   [3][world * cap / 256]
+ *   flags          int   [world], zero-initialised before the first step
+ * with cap = bucket_capacity rounded up to a multiple of 256 (>= the largest cloud any rank adds per step; world * cap
+ * <= max_points).  gem_tiled_step(r) = transform rank r's cloud, store every in-grid point into the OWNING rank's
+ * buffer over NVLink (slot = (r * cap / 256 + source block) * 256 + position in the block: deterministic, source
+ * order), raise rank r's flag on every peer; then, once every peer's flag of this step is up, bin and fold what
+ * arrived.  The result equals the single-GPU map of the rank-by-rank concatenated clouds bit for bit.  Steps are
+ * pipelined like gem_add_points_stream (gem_flush / gem_sync / any reading call issues the last fold); every rank
+ * must make the same sequence of gem_tiled_step calls. */
+typedef struct gem_tiled_peers {
+    int tiles_r, tiles_c, my_rank, bucket_capacity;
+    unsigned long long recv_records[64], recv_intensity[64], recv_counts[64], flags[64];
+} gem_tiled_peers;
+int gem_tiled_attach(gem_map *m, const gem_tiled_peers *peers);
+int gem_tiled_step(gem_map *m, const void *xyzi_device, const void *rgba_device, int n, const gem_frame *frame);
 
 #ifdef __cplusplus
 }
