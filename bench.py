@@ -251,6 +251,20 @@ def time_reference_gpu_kernels(frames, fobjs, L, res, nsteps=12):
     import ref_lib
     if not ref_lib.available(nofma=False):
         return {"unavailable": "oracle/_ref/libgpu_ref.so not built (needs /root/reference at build time)"}
+    # the reference prints to stdout from C (gpu_process.cu:988 "GPU Init mapping"): this process' stdout carries ONE JSON line
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        return _time_reference_gpu_kernels(ref_lib, frames, fobjs, L, res, nsteps)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+
+
+def _time_reference_gpu_kernels(ref_lib, frames, fobjs, L, res, nsteps):
     r = ref_lib.RefMap(L, res, nofma=False)
     F = len(frames)
     t_pp = t_fu = 0.0
