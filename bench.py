@@ -259,6 +259,11 @@ def time_reference_gpu_kernels(frames, fobjs, L, res, nsteps=12):
     try:
         return _time_reference_gpu_kernels(ref_lib, frames, fobjs, L, res, nsteps)
     finally:
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)   # the C library's own stdout buffer, while fd 1 still points at /dev/null
+        except Exception:
+            pass
         os.dup2(saved, 1)
         os.close(saved)
         os.close(devnull)
