@@ -152,10 +152,10 @@ def load_traffic(kernel: str):
 
 
 def best_cpu_threads(frames, L: int, res: float):
-    """the oracle's multi-threaded twin spawns its workers per call, so more threads is not always
-    faster: try a few counts on a short sample and keep the best (a fairer CPU baseline)"""
+    """the CPU port's best thread count on this box (persistent pool; a frame has ~0.1 ms of work per thread at 64
+    threads, so the barriers start to dominate somewhere): try a few counts on a short sample and keep the best"""
     ncpu = os.cpu_count() or 1
-    cands = sorted({t for t in (8, 16, 32, 64, ncpu) if t <= ncpu} | {min(ncpu, 8)})
+    cands = sorted({t for t in (8, 16, 32, 48, 64, 96, ncpu) if t <= ncpu} | {min(ncpu, 8)})
     best, best_v = cands[0], -1.0
     for t in cands:
         v, _, _ = cpu_baseline(frames, 4, t, L, res, warmup=1)
@@ -175,13 +175,13 @@ def cpu_baseline(frames, nsteps: int, threads: int, L: int, res: float, warmup: 
     for s in range(warmup):  # warm-up
         k = pingpong(s, F)
         o.move(frames[k]["position"])
-        o.add_mt(frames[k]["xyzi"], frames[k]["rgba"], fobjs[k], threads)
+        o.add_pool(frames[k]["xyzi"], frames[k]["rgba"], fobjs[k], threads)
     pts = 0
     t0 = time.perf_counter()
     for s in range(nsteps):
         k = pingpong(warmup + s, F)
         o.move(frames[k]["position"])
-        o.add_mt(frames[k]["xyzi"], frames[k]["rgba"], fobjs[k], threads)
+        o.add_pool(frames[k]["xyzi"], frames[k]["rgba"], fobjs[k], threads)
         pts += frames[k]["xyzi"].shape[0]
     dt = time.perf_counter() - t0
     o.close()
@@ -344,11 +344,11 @@ def cpu_baseline_c1(threads):
     for nt in (1, threads):
         o = OracleMap(200, 0.1, compat_box_filter=False)
         o.move(fr["position"])
-        o.add_mt(fr["xyzi"], fr["rgba"], f, nt)        # warm-up (first-touch of the layers)
+        o.add_pool(fr["xyzi"], fr["rgba"], f, nt)        # warm-up (first-touch of the layers, worker creation)
         reps = 20
         t0 = time.perf_counter()
         for _ in range(reps):
-            o.add_mt(fr["xyzi"], fr["rgba"], f, nt)
+            o.add_pool(fr["xyzi"], fr["rgba"], f, nt)
         dt = (time.perf_counter() - t0) / reps
         o.close()
         out[f"threads_{nt}"] = {"value": fr["xyzi"].shape[0] / dt / 1e6, "unit": "Mpoints/s", "ms_per_frame": dt * 1e3}

@@ -1166,7 +1166,7 @@ int gem_compute_features(gem_map *m)
     Lock lk(m->mu);
     SetDev sd(m->dev);
     { int rcf = flush_for_observer(m); if (rcf) return rcf; }
-    GEM_LAUNCH(m, GEM_PROF_FEATURES, k_features<false><<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, nullptr));
+    GEM_LAUNCH(m, GEM_PROF_FEATURES, k_features<false><<<dim3((m->geom.cols + FEAT_TILE - 1) / FEAT_TILE, (m->geom.rows + FEAT_TILE - 1) / FEAT_TILE), FEAT_TILE * FEAT_TILE, 0, m->stream>>>(m->geom, m->ml, nullptr));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }
@@ -1216,7 +1216,7 @@ int gem_compute_features_tiled(gem_map *m, const float *padded_elevation)
     Lock lk(m->mu);
     SetDev sd(m->dev);
     { int rcf = flush_for_observer(m); if (rcf) return rcf; }
-    GEM_LAUNCH(m, GEM_PROF_FEATURES, k_features<true><<<blocks_for(m->nc, 256, 1 << 30), 256, 0, m->stream>>>(m->geom, m->ml, padded_elevation));
+    GEM_LAUNCH(m, GEM_PROF_FEATURES, k_features<true><<<dim3((m->geom.cols + FEAT_TILE - 1) / FEAT_TILE, (m->geom.rows + FEAT_TILE - 1) / FEAT_TILE), FEAT_TILE * FEAT_TILE, 0, m->stream>>>(m->geom, m->ml, padded_elevation));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }

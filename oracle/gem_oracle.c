@@ -1051,3 +1051,179 @@ void orc_add_points_mt(orc_map *m, int n, const float *xyzi, const unsigned char
     pthread_barrier_destroy(&bar);
     free(th); free(ctx); free(key); free(geo); free(h); free(hv);
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* pooled multi-threaded CPU baseline: persistent workers, per-band point lists          */
+/* (bench.py cpu_baseline / --impl reference only).  Same results as orc_add_points_mt   */
+/* and as the single-threaded process_points + fuse (tests/test_oracle_kats.py).         */
+/*   phase 1  every thread transforms a contiguous slice of the cloud and counts, per     */
+/*            band of map rows, its points (storage rows for the fold, geographic rows    */
+/*            for the lowest layer);                                                      */
+/*   phase 2  the slice's point indices are written into the bands' lists: band-major,    */
+/*            then thread-major, then slice order = ascending point index inside a band   */
+/*            = the per-cell visiting order of G_fuse;                                    */
+/*   phase 3  bands are drawn from a shared counter (more bands than threads: the points  */
+/*            of a frame sit near the sensor) and folded by ONE thread each.              */
+/* ------------------------------------------------------------------------------------ */
+#include <stdatomic.h>
+struct orc_pool {
+    int nthreads, nbands;
+    pthread_t *th;
+    pthread_barrier_t bar;
+    int quit;
+    /* the job */
+    orc_map *m; int n;
+    const float *xyzi; const unsigned char *rgba; const float *T; double lo, hi; const orc_sensor *sensor; const float *sJ;
+    /* scratch */
+    int cap; int *key, *geo, *idxS, *idxG; float *h, *hv;
+    long *cntS, *cntG;   /* [nbands + 1][nthreads] -> offsets */
+    size_t cells; float *minh; int *amin; unsigned *seen; unsigned call_id;
+    atomic_int next_band;
+};
+typedef struct { orc_pool *p; int tid; } pool_arg;
+
+static int band_of(int row, int L, int nbands) { return (int)((long)row * nbands / L); }
+static void pool_job(orc_pool *p, int tid)
+{
+    static const float Z9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    static const float Z3[3] = {0, 0, 0};
+    orc_map *m = p->m;
+    const int L = m->L, nt = p->nthreads, nb = p->nbands;
+    const int lo_i = (int)((long)p->n * tid / nt), hi_i = (int)((long)p->n * (tid + 1) / nt);
+    int i, b;
+    for (b = 0; b < nb; b++) { p->cntS[(long)b * nt + tid] = 0; p->cntG[(long)b * nt + tid] = 0; }
+    for (i = lo_i; i < hi_i; i++) { /* phase 1 */
+        pt_result r;
+        process_one(m, p->xyzi[4 * i], p->xyzi[4 * i + 1], p->xyzi[4 * i + 2], p->T, p->lo, p->hi, p->sensor, p->sJ, Z9, Z9, Z3, Z9, &r);
+        p->key[i] = (r.key >= 0 && r.h != -1) ? r.key : -1;
+        p->geo[i] = r.accepted ? r.geo : -1;
+        p->h[i] = r.h;
+        p->hv[i] = r.hv;
+        if (p->key[i] >= 0) p->cntS[(long)band_of(p->key[i] / L, L, nb) * nt + tid]++;
+        if (p->geo[i] >= 0) p->cntG[(long)band_of(p->geo[i] / L, L, nb) * nt + tid]++;
+    }
+    pthread_barrier_wait(&p->bar);
+    if (tid == 0) { /* exclusive prefix in (band, thread) order */
+        long accS = 0, accG = 0, k, tot = (long)nb * nt;
+        for (k = 0; k < tot; k++) {
+            long c = p->cntS[k]; p->cntS[k] = accS; accS += c;
+            c = p->cntG[k]; p->cntG[k] = accG; accG += c;
+        }
+        p->cntS[tot] = accS; p->cntG[tot] = accG;
+        atomic_store(&p->next_band, 0);
+    }
+    pthread_barrier_wait(&p->bar);
+    { /* phase 2: this thread's slots of every band */
+        long *wS = (long *)malloc(sizeof(long) * nb), *wG = (long *)malloc(sizeof(long) * nb);
+        for (b = 0; b < nb; b++) { wS[b] = p->cntS[(long)b * nt + tid]; wG[b] = p->cntG[(long)b * nt + tid]; }
+        for (i = lo_i; i < hi_i; i++) {
+            if (p->key[i] >= 0) p->idxS[wS[band_of(p->key[i] / L, L, nb)]++] = i;
+            if (p->geo[i] >= 0) p->idxG[wG[band_of(p->geo[i] / L, L, nb)]++] = i;
+        }
+        free(wS); free(wG);
+    }
+    pthread_barrier_wait(&p->bar);
+    for (;;) { /* phase 3 */
+        long k, k0, k1, c;
+        int row_lo, row_hi;
+        b = atomic_fetch_add(&p->next_band, 1);
+        if (b >= nb) break;
+        k0 = p->cntS[(long)b * nt]; k1 = p->cntS[(long)(b + 1) * nt];
+        for (k = k0; k < k1; k++) {
+            int R = 0, G = 0, B = 0;
+            i = p->idxS[k];
+            if (p->rgba) { R = p->rgba[4 * i]; G = p->rgba[4 * i + 1]; B = p->rgba[4 * i + 2]; }
+            fuse_one(m, p->key[i], R, G, B, p->xyzi[4 * i + 3], p->h[i], p->hv[i]);
+        }
+        k0 = p->cntG[(long)b * nt]; k1 = p->cntG[(long)(b + 1) * nt];
+        for (k = k0; k < k1; k++) { /* lowest: minimum of the call and the first index attaining it (ORACLE DEFINITION) */
+            int g;
+            i = p->idxG[k]; g = p->geo[i];
+            if (p->seen[g] != p->call_id) { p->seen[g] = p->call_id; p->amin[g] = i; p->minh[g] = p->h[i]; }
+            else if (p->h[i] < p->minh[g]) { p->amin[g] = i; p->minh[g] = p->h[i]; }
+        }
+        for (k = k0; k < k1; k++) {
+            int g;
+            i = p->idxG[k]; g = p->geo[i];
+            if (p->amin[g] == i && p->minh[g] <= m->lowest[g]) m->lowest[g] = p->minh[g] + 3 * p->hv[i];
+        }
+        /* rows r with band_of(r) == b: [ceil(b L / nb), ceil((b + 1) L / nb)) */
+        row_lo = (int)(((long)b * L + nb - 1) / nb); row_hi = (int)(((long)(b + 1) * L + nb - 1) / nb);
+        for (c = (long)row_lo * L; c < (long)row_hi * L; c++) /* variance floor over the band (gpu.cu:533-534) */
+            if ((double)m->variance[c] < 0.0001) m->variance[c] = (float)0.0001;
+    }
+}
+static void *pool_worker(void *a)
+{
+    pool_arg *pa = (pool_arg *)a;
+    orc_pool *p = pa->p;
+    const int tid = pa->tid;
+    free(pa);
+    for (;;) {
+        pthread_barrier_wait(&p->bar); /* job posted */
+        if (p->quit) break;
+        pool_job(p, tid);
+        pthread_barrier_wait(&p->bar); /* job done */
+    }
+    return NULL;
+}
+orc_pool *orc_pool_create(int nthreads)
+{
+    orc_pool *p = (orc_pool *)calloc(1, sizeof(orc_pool));
+    int t;
+    if (nthreads < 1) nthreads = 1;
+    p->nthreads = nthreads;
+    p->th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
+    pthread_barrier_init(&p->bar, NULL, (unsigned)nthreads);
+    for (t = 1; t < nthreads; t++) {
+        pool_arg *a = (pool_arg *)malloc(sizeof(pool_arg));
+        a->p = p; a->tid = t;
+        pthread_create(&p->th[t], NULL, pool_worker, a);
+    }
+    return p;
+}
+void orc_pool_destroy(orc_pool *p)
+{
+    int t;
+    if (!p) return;
+    p->quit = 1;
+    pthread_barrier_wait(&p->bar);
+    for (t = 1; t < p->nthreads; t++) pthread_join(p->th[t], NULL);
+    pthread_barrier_destroy(&p->bar);
+    free(p->th); free(p->key); free(p->geo); free(p->idxS); free(p->idxG); free(p->h); free(p->hv);
+    free(p->cntS); free(p->cntG); free(p->minh); free(p->amin); free(p->seen);
+    free(p);
+}
+void orc_add_points_pool(orc_pool *p, orc_map *m, int n, const float *xyzi, const unsigned char *rgba, const float T[16],
+                         double relLower, double relUpper, const orc_sensor *sensor, const float sJ[3])
+{
+    const size_t cells = (size_t)m->L * m->L;
+    int nb = 8 * p->nthreads;
+    if (nb > m->L) nb = m->L;
+    if (n > p->cap) {
+        p->cap = n + n / 8 + 1024;
+        free(p->key); free(p->geo); free(p->idxS); free(p->idxG); free(p->h); free(p->hv);
+        p->key = (int *)malloc(sizeof(int) * p->cap); p->geo = (int *)malloc(sizeof(int) * p->cap);
+        p->idxS = (int *)malloc(sizeof(int) * p->cap); p->idxG = (int *)malloc(sizeof(int) * p->cap);
+        p->h = (float *)malloc(sizeof(float) * p->cap); p->hv = (float *)malloc(sizeof(float) * p->cap);
+    }
+    if (nb != p->nbands || !p->cntS) {
+        p->nbands = nb;
+        free(p->cntS); free(p->cntG);
+        p->cntS = (long *)malloc(sizeof(long) * ((size_t)nb * p->nthreads + 1));
+        p->cntG = (long *)malloc(sizeof(long) * ((size_t)nb * p->nthreads + 1));
+    }
+    if (cells != p->cells) {
+        p->cells = cells;
+        free(p->minh); free(p->amin); free(p->seen);
+        p->minh = (float *)malloc(sizeof(float) * cells); p->amin = (int *)malloc(sizeof(int) * cells);
+        p->seen = (unsigned *)calloc(cells, sizeof(unsigned));
+        p->call_id = 0;
+    }
+    p->call_id++;
+    if (p->call_id == 0) { memset(p->seen, 0, sizeof(unsigned) * cells); p->call_id = 1; }
+    p->m = m; p->n = n; p->xyzi = xyzi; p->rgba = rgba; p->T = T; p->lo = relLower; p->hi = relUpper; p->sensor = sensor; p->sJ = sJ;
+    pthread_barrier_wait(&p->bar); /* post */
+    pool_job(p, 0);
+    pthread_barrier_wait(&p->bar); /* done */
+}

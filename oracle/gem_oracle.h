@@ -150,6 +150,14 @@ void orc_add_points_mt(orc_map *m, int n, const float *xyzi /* n*4 */, const uns
                        const float T[16], double relLower, double relUpper,
                        const orc_sensor *sensor, const float sJ[3], int nthreads);
 
+/* pooled variant of orc_add_points_mt: persistent worker threads, per-band point lists, dynamic band assignment
+ * (bench.py's CPU baseline; same results) */
+typedef struct orc_pool orc_pool;
+orc_pool *orc_pool_create(int nthreads);
+void orc_pool_destroy(orc_pool *p);
+void orc_add_points_pool(orc_pool *p, orc_map *m, int n, const float *xyzi, const unsigned char *rgba, const float T[16],
+                         double relLower, double relUpper, const orc_sensor *sensor, const float sJ[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,10 @@ def load():
     lib.orc_clean_point_cloud.restype = C.c_int
     lib.orc_clean_point_cloud.argtypes = [C.POINTER(OrcSensor), C.c_int, P, P]
     lib.orc_add_points_mt.argtypes = [MP, C.c_int, P, P, P, C.c_double, C.c_double, C.POINTER(OrcSensor), P, C.c_int]
+    lib.orc_pool_create.restype = P
+    lib.orc_pool_create.argtypes = [C.c_int]
+    lib.orc_pool_destroy.argtypes = [P]
+    lib.orc_add_points_pool.argtypes = [P, MP, C.c_int, P, P, P, C.c_double, C.c_double, C.POINTER(OrcSensor), P]
     _lib = lib
     return lib
 
@@ -116,6 +120,8 @@ class OracleMap:
         self.shape = (self.length, self.length)
 
     def close(self):
+        for pool in self.__dict__.pop("_pools", {}).values():
+            self.lib.orc_pool_destroy(pool)
         if self.m:
             self.lib.orc_destroy(self.m)
             self.m = None
@@ -196,6 +202,18 @@ class OracleMap:
         sensor = sensor_from_frame(frame)
         self.lib.orc_add_points_mt(self.m, xyzi.shape[0], _p(xyzi), _p(rgba), _p(T), frame.rel_lower, frame.rel_upper,
                                    C.byref(sensor), _p(sJ), int(nthreads))
+
+    def add_pool(self, xyzi, rgba, frame, nthreads):
+        """pooled CPU baseline: persistent worker threads (created on first use, per thread count)"""
+        xyzi, rgba = self.clean_point_cloud(xyzi, rgba, frame)
+        pools = self.__dict__.setdefault("_pools", {})
+        if nthreads not in pools:
+            pools[nthreads] = self.lib.orc_pool_create(int(nthreads))
+        T = np.array(frame.T[:], np.float32)
+        sJ = np.array(frame.sensor_jacobian[:], np.float32)
+        sensor = sensor_from_frame(frame)
+        self.lib.orc_add_points_pool(pools[nthreads], self.m, xyzi.shape[0], _p(xyzi), _p(rgba), _p(T), frame.rel_lower,
+                                     frame.rel_upper, C.byref(sensor), _p(sJ))
 
     def var_update(self, dv):
         self.lib.orc_var_update(self.m, float(dv))

@@ -25,6 +25,36 @@ def compile_program():
     return EXE
 
 
+THREADS_EXE = os.path.join(ROOT, "tests", "cxx", "threads_shim")
+
+
+def compile_threads_program():
+    lib = build.build()
+    srcs = [os.path.join(ROOT, "tests", "cxx", "threads_shim.cpp"), os.path.join(ROOT, "compat", "gpu_process_shim.cpp")]
+    deps = srcs + [lib, os.path.join(ROOT, "include", "gem_b200.h")]
+    if os.path.exists(THREADS_EXE) and all(os.path.getmtime(d) <= os.path.getmtime(THREADS_EXE) for d in deps):
+        return THREADS_EXE
+    cmd = ["g++", "-O2", "-std=c++14", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle", "mini_eigen"),
+           "-o", THREADS_EXE] + srcs + ["-L", os.path.dirname(lib), "-lgem_b200", "-Wl,-rpath," + os.path.dirname(lib)]
+    subprocess.run(cmd, check=True)
+    return THREADS_EXE
+
+
+def test_three_thread_program_compiles():
+    assert os.path.exists(compile_threads_program())
+
+
+@pytest.mark.gpu
+def test_node_threading_through_the_shim():
+    """the node's three threads (Process_points outside MapMutex_, ElevationMapping.cpp:271-282) through the unmodified
+    shim: no failures, sane map"""
+    exe = compile_threads_program()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr[-2000:])
+    assert r.returncode == 0 and "failures=0" in r.stdout, r.stdout + r.stderr[-2000:]
+    assert "failed" not in r.stderr
+
+
 def test_facade_and_shim_compile_and_link():
     exe = compile_program()
     assert os.path.exists(exe)

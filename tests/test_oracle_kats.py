@@ -297,6 +297,24 @@ def test_mt_baseline_twin_equals_single_thread():
         assert np.array_equal(a.get_layer(name), b.get_layer(name)), name
 
 
+def test_pooled_baseline_equals_single_thread():
+    """bench.py's CPU baseline (persistent pool, per-band point lists, dynamic band assignment) == the plain oracle,
+    over several frames with scrolling, for thread counts that do and do not divide the map"""
+    frs = [synth.hdl64_frame(k) for k in range(3)]
+    for nt in (1, 3, 8):
+        a = OracleMap(200, 0.1, compat_box_filter=False)
+        b = OracleMap(200, 0.1, compat_box_filter=False)
+        for fr in frs:
+            f = gem_b200.make_frame(fr["T"], gem_b200.LaserSensorProcessor())
+            for m in (a, b):
+                m.move(fr["position"])
+            a.add(fr["xyzi"], fr["rgba"], f)
+            b.add_pool(fr["xyzi"], fr["rgba"], f, nt)
+            for name in ("elevation", "variance", "intensity", "color_r", "color_g", "color_b", "lowest"):
+                assert np.array_equal(a.get_layer(name), b.get_layer(name)), (nt, name)
+        a.close(); b.close()
+
+
 def test_colourise_kats():
     """ElevationMapping.cpp:331-381: pinhole projection, strict image-bound test, intensity zeroing"""
     import oracle_lib
