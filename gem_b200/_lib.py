@@ -95,6 +95,8 @@ SYMBOLS = {
     "gem_closeloop": (C.c_int, [_P, _FP, C.c_float]),
     "gem_colourise_points": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _P, C.c_int, C.c_int, C.c_int, _P]),
     "gem_export_layers": (C.c_int, [_P, C.POINTER(_P)]),
+    "gem_export_layers_begin": (C.c_int, [_P, C.POINTER(_P)]),
+    "gem_export_layers_end": (C.c_int, [_P]),
     "gem_get_layer": (C.c_int, [_P, C.c_int, _P]),
     "gem_set_layer": (C.c_int, [_P, C.c_int, _P]),
     "gem_get_state": (C.c_int, [_P, _FP, _IP, _FP]),
@@ -116,6 +118,8 @@ SYMBOLS = {
     "gem_route_points_peer": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame), C.c_int, C.c_int,
                                         C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int, C.c_int]),
     "gem_fuse_records_counted": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
+    "gem_transform_cloud": (C.c_int, [_P, _P, C.c_int, _FP]),
+    "gem_refuse_submaps": (C.c_int, [_P, _P, _IP, _P, _IP, C.c_double, C.c_int, _IP]),
     "gem_tiled_attach": (C.c_int, [_P, C.POINTER(GemTiledPeers)]),
     "gem_tiled_step": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(GemFrame)]),
 }

@@ -25,6 +25,7 @@
 #include "gem_add.cuh"
 #include "gem_kernels.cuh"
 #include "gem_route.cuh"
+#include "gem_submap.cuh"
 
 using namespace gem;
 
@@ -113,6 +114,7 @@ struct gem_map {
     BinCounters *h_ctr = nullptr; // pinned
     // pipelined host ingest (gem_add_points_host_async): three staging sets (the fold of call i, issued with
     // call i+1, still reads call i's intensities)
+    cudaEvent_t ev_export = nullptr, ev_export_done = nullptr; // gem_export_layers_begin / _end
     cudaStream_t copy_stream = nullptr;
     void *d_axyzi[3] = {nullptr, nullptr, nullptr}, *d_argba[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_h2d[3] = {nullptr, nullptr, nullptr}, ev_done[3] = {nullptr, nullptr, nullptr};
@@ -421,6 +423,7 @@ int ensure_compat_staging(gem_map *m)
 }
 int ensure_out_staging(gem_map *m)
 {
+    if (m->ev_export_done) cudaStreamWaitEvent(m->stream, m->ev_export_done, 0); // an asynchronous export may still be reading the staging buffer
     if (m->d_out) return GEM_OK;
     return dev_alloc(m, &m->d_out, m->nc * 9);
 }
@@ -760,6 +763,8 @@ int gem_destroy(gem_map *m)
             if (m->ev_fold[i]) cudaEventDestroy(m->ev_fold[i]);
         }
         if (m->ev_mark) cudaEventDestroy(m->ev_mark);
+        if (m->ev_export) cudaEventDestroy(m->ev_export);
+        if (m->ev_export_done) cudaEventDestroy(m->ev_export_done);
         if (m->front_stream) cudaStreamDestroy(m->front_stream);
         for (int i = 0; i < 4; i++) if (m->ev_frames[i]) cudaEventDestroy(m->ev_frames[i]);
         for (int i = 0; i < 3; i++) {
@@ -1341,6 +1346,43 @@ int gem_export_layers(gem_map *m, float *host_layers[9])
     return GEM_OK;
 }
 
+// The write-back in two halves: _begin runs the export kernel and starts the device-to-host copies on the copy stream,
+// _end waits for them.  Between the two the caller can issue work that does not change what was exported -- the node
+// calls Raytracing right after Map_feature + show() (ElevationMapping.cpp:404-421), and the ray clean-up does not
+// touch the staging buffer -- so the 4 * 9 * L^2 bytes cross PCIe while the rays are traced.
+int gem_export_layers_begin(gem_map *m, float *host_layers[9])
+{
+    if (!m || !host_layers) return GEM_ERR_INVALID;
+    if (m->geom.tiled) return fail(m, GEM_ERR_INVALID, "gem_export_layers_begin: not available on tiled handles");
+    Lock lk(m->mu);
+    SetDev sd(m->dev);
+    int rc = ensure_out_staging(m);
+    if (rc) return rc;
+    if ((rc = flush_for_observer(m))) return rc;
+    if (!m->copy_stream) GEM_CUDA(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    if (!m->ev_export) GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_export, cudaEventDisableTiming));
+    if (!m->ev_export_done) GEM_CUDA(m, cudaEventCreateWithFlags(&m->ev_export_done, cudaEventDisableTiming));
+    dim3 grid((m->L + 31) / 32, (m->L + 31) / 32);
+    GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_export_done, 0)); // the previous export's copies have left the staging buffer
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_export_colmajor<<<grid, 256, 0, m->stream>>>(m->ml, m->L, m->d_out));
+    GEM_CUDA(m, cudaGetLastError());
+    GEM_CUDA(m, cudaEventRecord(m->ev_export, m->stream));
+    GEM_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->ev_export, 0));
+    for (int k = 0; k < 9; k++)
+        if (host_layers[k])
+            GEM_CUDA(m, cudaMemcpyAsync(host_layers[k], m->d_out + (size_t)k * m->nc, m->nc * 4, cudaMemcpyDeviceToHost, m->copy_stream));
+    GEM_CUDA(m, cudaEventRecord(m->ev_export_done, m->copy_stream));
+    return GEM_OK;
+}
+int gem_export_layers_end(gem_map *m)
+{
+    if (!m) return GEM_ERR_INVALID;
+    Lock lk(m->mu);
+    SetDev sd(m->dev);
+    if (m->ev_export_done) GEM_CUDA(m, cudaEventSynchronize(m->ev_export_done));
+    return GEM_OK;
+}
+
 int gem_export_orthomosaic(gem_map *m, unsigned char *host_bgr)
 {
     if (!m || !host_bgr) return fail(m, GEM_ERR_INVALID, "gem_export_orthomosaic: null argument");
@@ -1616,6 +1658,64 @@ int gem_route_points_peer(gem_map *m, const void *xyzi, const void *rgba, int n,
     m->launches += 3;
     if (e != cudaSuccess) return fail(m, GEM_ERR_CUDA, std::string("gem_route_points_peer: ") + cudaGetErrorString(e));
     return GEM_OK;
+}
+
+// ---- loop-closure submap re-fusion (gem_submap.cuh) -------------------------------------------------------
+int gem_transform_cloud(gem_map *m, void *points32, int n, const float T[16])
+{
+    if (!m || n < 0 || (n > 0 && !points32) || !T) return fail(m, GEM_ERR_INVALID, "gem_transform_cloud: bad argument");
+    Lock lk(m->mu);
+    SetDev sd(m->dev);
+    Rigid r;
+    for (int i = 0; i < 12; i++) r.t[i] = T[i];
+    if (n > 0) GEM_LAUNCH(m, GEM_PROF_OTHER, k_transform_cloud<<<blocks_for((size_t)n, 256, 1 << 30), 256, 0, m->stream>>>((SubPoint *)points32, n, r));
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
+int gem_refuse_submaps(gem_map *m, void *new_points32, int *n_new, void *old_points32, int *n_old, double resolution, int compat,
+                       int *fused_out)
+{
+    if (!m || !n_new || !n_old || *n_new < 0 || *n_old < 0 || (*n_new > 0 && !new_points32) || (*n_old > 0 && !old_points32) || !(resolution > 0.0))
+        return fail(m, GEM_ERR_INVALID, "gem_refuse_submaps: bad argument");
+    Lock lk(m->mu);
+    SetDev sd(m->dev);
+    const int nn = *n_new, no = *n_old;
+    auto pow2 = [](size_t v) { size_t p = 64; while (p < v) p <<= 1; return p; };
+    const size_t cn = pow2(2 * (size_t)nn + 2), co = pow2(2 * (size_t)no + 2);
+    // one scratch block: two hash tables (keys + first index), keep flags, compaction outputs, counters
+    const size_t bytes = (cn + co) * (8 + 4) + (size_t)nn + no + 64 + ((size_t)nn + no) * sizeof(SubPoint) + 64;
+    char *d = nullptr;
+    GEM_CUDA(m, cudaMalloc((void **)&d, bytes));
+    unsigned long long *kn = (unsigned long long *)d, *ko = kn + cn;
+    int *fn = (int *)(ko + co), *fo = fn + cn;
+    int *cnts = fo + co; // [0] fused, [1] kept new, [2] kept old
+    SubPoint *outn = (SubPoint *)(((uintptr_t)(cnts + 4) + 31) & ~(uintptr_t)31), *outo = outn + nn;
+    unsigned char *keepn = (unsigned char *)(outo + no), *keepo = keepn + nn;
+    auto done = [&](int rc) { cudaFree(d); return rc; };
+    cudaError_t e = cudaMemsetAsync(kn, 0xff, (cn + co) * 8, m->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fn, 0x7f, (cn + co) * 4, m->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cnts, 0, 16, m->stream);
+    if (e != cudaSuccess) return done(fail(m, GEM_ERR_CUDA, cudaGetErrorString(e)));
+    SubPoint *pn = (SubPoint *)new_points32, *po = (SubPoint *)old_points32;
+    if (nn) GEM_LAUNCH(m, GEM_PROF_OTHER, k_hash_insert<<<blocks_for((size_t)nn, 256, 1 << 30), 256, 0, m->stream>>>(pn, nn, resolution, kn, fn, (unsigned)(cn - 1)));
+    if (no) GEM_LAUNCH(m, GEM_PROF_OTHER, k_hash_insert<<<blocks_for((size_t)no, 256, 1 << 30), 256, 0, m->stream>>>(po, no, resolution, ko, fo, (unsigned)(co - 1)));
+    const int nmax = nn > no ? nn : no;
+    if (nmax) GEM_LAUNCH(m, GEM_PROF_OTHER, k_refuse_pair<<<blocks_for((size_t)nmax, 256, 1 << 30), 256, 0, m->stream>>>(pn, nn, po, no, resolution, kn, fn, (unsigned)(cn - 1), ko, fo, (unsigned)(co - 1), keepn, keepo, compat, cnts));
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_points<<<1, 1024, 0, m->stream>>>(pn, keepn, nn, outn, cnts + 1));
+    GEM_LAUNCH(m, GEM_PROF_OTHER, k_compact_points<<<1, 1024, 0, m->stream>>>(po, keepo, no, outo, cnts + 2));
+    int h[4] = {0, 0, 0, 0};
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, cnts, 16, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e == cudaSuccess && h[1] > 0) e = cudaMemcpyAsync(pn, outn, (size_t)h[1] * sizeof(SubPoint), cudaMemcpyDeviceToDevice, m->stream);
+    if (e == cudaSuccess && h[2] > 0) e = cudaMemcpyAsync(po, outo, (size_t)h[2] * sizeof(SubPoint), cudaMemcpyDeviceToDevice, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) return done(fail(m, GEM_ERR_CUDA, std::string("gem_refuse_submaps: ") + cudaGetErrorString(e)));
+    *n_new = h[1];
+    *n_old = h[2];
+    if (fused_out) *fused_out = h[0];
+    return done(GEM_OK);
 }
 
 // ---- tiled maps, peer path (gem_route.cuh "Peer path, round 2") --------------------------------------------------------

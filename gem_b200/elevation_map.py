@@ -329,6 +329,16 @@ class ElevationMap:
         check(self._lib.gem_export_layers(self._h, ptrs), self._h, "gem_export_layers")
         return out
 
+    def export_layers_begin(self, out: dict, names=None):
+        """asynchronous write-back into PINNED Fortran-ordered arrays (names: subset of the 9 layers, default all);
+        finish with export_layers_end()"""
+        names = _lib.EXPORT_LAYERS if names is None else names
+        ptrs = (C.c_void_p * 9)(*[(out[n].ctypes.data if n in names else None) for n in _lib.EXPORT_LAYERS])
+        check(self._lib.gem_export_layers_begin(self._h, ptrs), self._h, "gem_export_layers_begin")
+
+    def export_layers_end(self):
+        check(self._lib.gem_export_layers_end(self._h), self._h, "gem_export_layers_end")
+
     def get_layer(self, name: str) -> np.ndarray:
         lid = _lib.LAYERS[name]
         arr = np.empty(self.ncells, np.int32 if lid in _lib.INT_LAYERS else np.float32)
@@ -436,6 +446,18 @@ class ElevationMap:
     def fuse_records_counted(self, rec, src_counts, n_sources: int, bucket_stride: int):
         rc = self._lib.gem_fuse_records_counted(self._h, _ptr(rec), _ptr(src_counts), int(n_sources), int(bucket_stride))
         check(rc, self._h, "gem_fuse_records_counted")
+
+    def transform_cloud(self, points32, T):
+        """gem_transform_cloud: (n, 8) float32 device tensor of PointXYZRGBICT records, rigidly transformed in place"""
+        t = (C.c_float * 16)(*[float(v) for v in np.asarray(T, np.float32).reshape(-1)])
+        check(self._lib.gem_transform_cloud(self._h, _ptr(points32), int(points32.shape[0]), t), self._h, "gem_transform_cloud")
+
+    def refuse_submaps(self, new_points32, old_points32, resolution: float, compat: bool = True):
+        """gem_refuse_submaps on two (n, 8) float32 device tensors; returns (n_new, n_old, fused): the tensors' first n rows hold the result"""
+        nn, no, fused = C.c_int(int(new_points32.shape[0])), C.c_int(int(old_points32.shape[0])), C.c_int(0)
+        check(self._lib.gem_refuse_submaps(self._h, _ptr(new_points32), C.byref(nn), _ptr(old_points32), C.byref(no), float(resolution),
+                                           1 if compat else 0, C.byref(fused)), self._h, "gem_refuse_submaps")
+        return nn.value, no.value, fused.value
 
     def tiled_attach(self, tiles_r, tiles_c, my_rank, bucket_capacity, recv_records, recv_intensity, recv_counts, flags):
         """gem_tiled_attach: lists of device addresses (ints), one per rank, of the four peer-accessible buffers"""

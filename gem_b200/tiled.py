@@ -263,7 +263,8 @@ def parity_check(mode: str = "peer", steps: int = 3, L_per_rank: int = 512, res:
         fr["T"][:2, 3] = (ox * 0.5 + s, oy * 0.5)
         return fr, gem_b200.make_frame(fr["T"], gem_b200.LaserSensorProcessor())
 
-    tm = TiledElevationMap(L, res, max_points=1 << 20, bucket_capacity=0 if mode == "packed" else (1 << 17) + 4096,
+    cap = (1 << 17) + 4096
+    tm = TiledElevationMap(L, res, max_points=max(1 << 20, world * cap), bucket_capacity=0 if mode == "packed" else cap,
                            peer=(mode == "peer"))
     keep = []
     for s in range(steps):
@@ -327,6 +328,13 @@ def sensor_offset(rank: int, world: int):
     return (i - (tr - 1) / 2.0) * 50.0, (j - (tc - 1) / 2.0) * 50.0
 
 
+def tile_centre_offset(rank: int, world: int, L: int, res: float):
+    """the balanced rig: every sensor at the centre of its own rank's tile (map coordinates; index 0 is the highest
+    coordinate, gpu_process.cu:316-317)"""
+    r0, nr, c0, nc = tile_of_rank(rank, world, L)
+    return (L / 2.0 - (r0 + nr / 2.0)) * res, (L / 2.0 - (c0 + nc / 2.0)) * res
+
+
 def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, algo_bytes_per_point):
     import json
     import torch
@@ -344,17 +352,21 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
     F = int(max(2, args.frames))   # per-GPU inputs larger than L2 whatever --steps is
     # every rank drives its own sensor: same scene generator, different seeds/poses
     frames = gen_frames(F, first=1000 * rank)
-    ox, oy = sensor_offset(rank, world)
     half = F / 2.0
-    fobjs, pos = [], []
-    for k, fr in enumerate(frames):
-        T = fr["T"].copy()
-        T[0, 3] = ox + (k - half)        # 1 m per frame along +x, centred on the rig position
-        T[1, 3] = oy
-        fr2 = dict(fr)
-        fr2["T"] = T
-        fobjs.append(laser_frame(fr2))
-        pos.append(np.array([T[0, 3], T[1, 3], T[2, 3]]))
+
+    def rig(ox, oy):
+        fo, po = [], []
+        for k, fr in enumerate(frames):
+            T = fr["T"].copy()
+            T[0, 3] = ox + (k - half)        # 1 m per frame along +x, centred on the rig position
+            T[1, 3] = oy
+            fr2 = dict(fr)
+            fr2["T"] = T
+            fo.append(laser_frame(fr2))
+            po.append(np.array([T[0, 3], T[1, 3], T[2, 3]]))
+        return fo, po
+    fobjs, pos = rig(*sensor_offset(rank, world))                          # SURVEY 8d rig: the headline
+    fobjs_bal, _ = rig(*tile_centre_offset(rank, world, L, res))           # one sensor at the centre of every tile
     dev = torch.device("cuda", local)
     npts = [fr["xyzi"].shape[0] for fr in frames]
     xyzi_d = [torch.from_numpy(fr["xyzi"]).to(dev) for fr in frames]
@@ -409,6 +421,25 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
     torch.cuda.synchronize()
     launches = tm.map.profile_read(reset=True)["launches"]
     last_stats = tm.map.stats()
+    # ---- the same steps with a balanced rig (SURVEY's rig leaves the outer tiles of a 2 x 4 split without a sensor:
+    # at 8 GPUs four ranks fold two sensors' points each and four fold almost none) ----
+    for s in range(10):
+        k = pingpong(s, F); tm.add(xyzi_d[k], rgba_d[k], fobjs_bal[k])
+    tm.map.sync(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    Kb = min(K, 300)
+    bpts = 0
+    e0.record(stream)
+    for s in range(Kb):
+        k = pingpong(10 + s, F); tm.add(xyzi_d[k], rgba_d[k], fobjs_bal[k]); bpts += npts[k]
+    tm.map.flush()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    bms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    btot = torch.tensor([float(bpts)], device=dev, dtype=torch.float64)
+    dist.all_reduce(bms, op=dist.ReduceOp.MAX); dist.all_reduce(btot, op=dist.ReduceOp.SUM)
+    balanced = {"value": float(btot.item()) / (float(bms.item()) * 1e-3) / 1e6, "unit": "Mpoints/s", "ms_per_step": float(bms.item()) / Kb,
+                "steps": Kb, "rig": "one sensor at the centre of every rank's tile (every rank folds one sensor's points)"}
+    bal_stats = tm.map.stats()
     tot = torch.tensor([float(pts), float(launches)], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -468,7 +499,8 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
             "e2e": e2e,
             "clocks": clocks, "gpu_launches": int(tot[1].item()),
             "tiled_parity": parity,
-            "extra": {"rank0_last_step_stats": last_stats},
+            "extra": {"rank0_last_step_stats": last_stats, "balanced_rig": balanced, "rank0_last_step_stats_balanced": bal_stats,
+                      "rig": "SURVEY 8d: sensors 50 m apart on a tiles_r x tiles_c rig centred on the map"},
         }
     dist.barrier()
     dist.destroy_process_group()

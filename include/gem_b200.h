@@ -223,6 +223,11 @@ int gem_colourise_points(gem_map *m, void *xyzi_device, int n, const double T_ca
  * storage indexed, NaN where the reference leaves the cell cleared (elevation == -10 or
  * traver == -10 or traver is NaN, ElevationMap.cpp:101).  host_layers[k] may be NULL. */
 int gem_export_layers(gem_map *m, float *host_layers[9]);
+/* the same in two halves: _begin returns once the copies are under way (pinned host memory!), _end waits for them.
+ * Calls that do not change the exported state may be made in between -- the node's next call after show() is
+ * Raytracing (ElevationMapping.cpp:404-421) -- so the 36 * L^2 bytes cross PCIe under the ray clean-up. */
+int gem_export_layers_begin(gem_map *m, float *host_layers[9]);
+int gem_export_layers_end(gem_map *m);
 
 /* The other two products of ElevationMap::show, from the same pass's state (call after gem_compute_features):
  * gem_export_orthomosaic: the bgr8 image of ElevationMap.cpp:87,123-125, L x L x 3 bytes row-major; a shown cell
@@ -326,6 +331,25 @@ int gem_route_points_peer(gem_map *m, const void *xyzi_device, const void *rgba_
  * src_counts_device[s] */
 int gem_fuse_records_counted(gem_map *m, const void *rec_device, const int *src_counts_device, int n_sources,
                              int bucket_stride);
+
+/* ---- loop-closure re-fusion of submaps (ElevationMapping::updateGlobalMap, ElevationMapping.cpp:773-905) ----
+ * Submaps are arrays of 32-byte PointXYZRGBICT records in device memory (what gem_harvest_scrolled_out produces).
+ * gem_transform_cloud: the rigid re-transform of :805 (pcl::transformPointCloud with T = optimised pose * old pose^-1,
+ *   row-major 4 x 4; x' = t00 x + t01 y + t02 z + t03 evaluated left to right in float), in place.
+ * gem_refuse_submaps: one pass of the pairwise loop :847-883 for the pair (new = the neighbour, old = submap i): both clouds
+ *   are reduced to one point per cell (pointCloudtoHash :1180-1192: cell = (ceil(x / res) * res - res / 2, same for y) in
+ *   double -> float, the FIRST point of a cell wins), every cell present in both whose OLD variance lies in (0, 1) gets the
+ *   fused elevation / variance in both clouds together with the new cloud's colour, intensity and traversability, and both
+ *   clouds come back compacted in place (x, y = the cell's position, w = 1; *n_new / *n_old updated; first-occurrence order).
+ *   compat != 0 evaluates the fused values exactly as the reference's expression parses (:862-863: var_n^2 e_o + (var_o^2 e_n) /
+ *   var_o^2 + var_n^2, and var_o^2 var_n^2 / var_o^2 + var_n^2), compat == 0 the weighting it was written for
+ *   ((var_n^2 e_o + var_o^2 e_n) / (var_o^2 + var_n^2), var_o^2 var_n^2 / (var_o^2 + var_n^2)), all in double like pow().
+ *   Definitions where the reference is implementation-defined (unordered_map iteration while erasing / inserting, uninitialised
+ *   point fields): DESIGN.md "f4".  Host-synchronous.  The kd-tree neighbour selection of :821-838 stays with the caller
+ *   (a handful of submap centres). */
+int gem_transform_cloud(gem_map *m, void *points32_device, int n, const float T[16]);
+int gem_refuse_submaps(gem_map *m, void *new_points32_device, int *n_new, void *old_points32_device, int *n_old, double resolution,
+                       int compat, int *fused_out);
 
 /* ---- tiled maps, peer path: one kernel routes AND exchanges (no collective library, no barrier kernel) ----------
  * The caller allocates, on every rank, four peer-accessible buffers (e.g. CUDA IPC / torch symmetric memory; the

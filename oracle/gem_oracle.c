@@ -1227,3 +1227,102 @@ void orc_add_points_pool(orc_pool *p, orc_map *m, int n, const float *xyzi, cons
     pool_job(p, 0);
     pthread_barrier_wait(&p->bar); /* done */
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* loop-closure submap re-fusion: ElevationMapping::updateGlobalMap, ElevationMapping.cpp:773-905                      */
+/* (PARITY UNPINNED: needs PCL / ROS; restated from the source, with the DEFINITIONS of DESIGN.md "f4" where the        */
+/* reference depends on unordered_map iteration order or uninitialised fields).  Points are 8 floats:                   */
+/* {x, y, z, w, bgra bits, covariance, intensity, travers} (PointXYZRGBICT.hpp:26-48).                                   */
+/* ------------------------------------------------------------------------------------ */
+void orc_transform_cloud(float *pts, int n, const float T[16])
+{ /* :805 pcl::transformPointCloud, scalar form, left to right */
+    int i;
+    for (i = 0; i < n; i++) {
+        float x = pts[8 * i], y = pts[8 * i + 1], z = pts[8 * i + 2];
+        pts[8 * i] = ((T[0] * x + T[1] * y) + T[2] * z) + T[3];
+        pts[8 * i + 1] = ((T[4] * x + T[5] * y) + T[6] * z) + T[7];
+        pts[8 * i + 2] = ((T[8] * x + T[9] * y) + T[10] * z) + T[11];
+    }
+}
+typedef struct { float rx, ry; int idx; } cell_ref;
+static int cell_cmp(const void *a, const void *b)
+{
+    const cell_ref *p = (const cell_ref *)a, *q = (const cell_ref *)b;
+    if (p->rx != q->rx) return p->rx < q->rx ? -1 : 1;
+    if (p->ry != q->ry) return p->ry < q->ry ? -1 : 1;
+    return p->idx < q->idx ? -1 : (p->idx > q->idx);
+}
+/* the cells of a cloud: sorted (cell, first index) table of the non-NaN points; keep[i] = 1 for the first point of every
+ * cell (and for NaN-positioned points, which equal nothing) */
+static int build_cells(const float *pts, int n, double res, cell_ref *tab, unsigned char *keep, float *rxs, float *rys)
+{
+    int i, m = 0, u = 0;
+    for (i = 0; i < n; i++) { /* pointCloudtoHash :1183-1184 */
+        float rx = (float)(ceil((double)pts[8 * i] / res) * res - res / 2.0);
+        float ry = (float)(ceil((double)pts[8 * i + 1] / res) * res - res / 2.0);
+        rxs[i] = rx; rys[i] = ry;
+        keep[i] = 0;
+        if (rx != rx || ry != ry) { keep[i] = 1; continue; }
+        tab[m].rx = rx; tab[m].ry = ry; tab[m].idx = i; m++;
+    }
+    qsort(tab, (size_t)m, sizeof(cell_ref), cell_cmp);
+    for (i = 0; i < m; i++) /* insert() keeps the first point of a cell */
+        if (i == 0 || tab[i].rx != tab[i - 1].rx || tab[i].ry != tab[i - 1].ry) { keep[tab[i].idx] = 1; tab[u++] = tab[i]; }
+    return u;
+}
+static int find_cell(const cell_ref *tab, int m, float rx, float ry)
+{
+    int lo = 0, hi = m - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) / 2;
+        if (tab[mid].rx == rx && tab[mid].ry == ry) return tab[mid].idx;
+        if (tab[mid].rx < rx || (tab[mid].rx == rx && tab[mid].ry < ry)) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+static int compact_kept(float *pts, int n, const unsigned char *keep, const float *rxs, const float *rys)
+{
+    int i, k = 0;
+    for (i = 0; i < n; i++)
+        if (keep[i]) {
+            if (k != i) memcpy(pts + 8 * k, pts + 8 * i, 32);
+            pts[8 * k] = rxs[i]; pts[8 * k + 1] = rys[i]; pts[8 * k + 3] = 1.0f; /* localHashtoPointCloud :1129-1130 */
+            k++;
+        }
+    return k;
+}
+int orc_refuse_submaps(float *pn, int *n_new, float *po, int *n_old, double res, int compat)
+{
+    const int nn = *n_new, no = *n_old;
+    cell_ref *tn = (cell_ref *)malloc(sizeof(cell_ref) * (size_t)(nn + 1)), *to = (cell_ref *)malloc(sizeof(cell_ref) * (size_t)(no + 1));
+    unsigned char *kn = (unsigned char *)malloc((size_t)nn + 1), *ko = (unsigned char *)malloc((size_t)no + 1);
+    float *rxn = (float *)malloc(4 * (size_t)(nn + 1)), *ryn = (float *)malloc(4 * (size_t)(nn + 1));
+    float *rxo = (float *)malloc(4 * (size_t)(no + 1)), *ryo = (float *)malloc(4 * (size_t)(no + 1));
+    const int mo = build_cells(po, no, res, to, ko, rxo, ryo);
+    int i, count = 0;
+    (void)build_cells(pn, nn, res, tn, kn, rxn, ryn);
+    for (i = 0; i < nn; i++) { /* every cell of the new map, once (:847) */
+        int j;
+        if (!kn[i] || rxn[i] != rxn[i] || ryn[i] != ryn[i]) continue;
+        j = find_cell(to, mo, rxn[i], ryn[i]);
+        if (j >= 0 && po[8 * j + 5] > 0 && po[8 * j + 5] < 1) { /* :857 */
+            const float vo = po[8 * j + 5], eo = po[8 * j + 2], vn = pn[8 * i + 5], en = pn[8 * i + 2];
+            const double vn2 = pow((double)vn, 2), vo2 = pow((double)vo, 2);
+            float ef, vf;
+            if (compat) { /* :862-863, as written */
+                ef = (float)(vn2 * eo + vo2 * en / vo2 + vn2);
+                vf = (float)(vo2 * vn2 / vo2 + vn2);
+            } else {
+                ef = (float)((vn2 * eo + vo2 * en) / (vo2 + vn2));
+                vf = (float)(vo2 * vn2 / (vo2 + vn2));
+            }
+            pn[8 * i + 2] = ef; pn[8 * i + 5] = vf;
+            memcpy(po + 8 * j, pn + 8 * i, 32); /* tmp_data is built from the NEW map's entry (:856) and inserted into both */
+            count++;
+        }
+    }
+    *n_new = compact_kept(pn, nn, kn, rxn, ryn);
+    *n_old = compact_kept(po, no, ko, rxo, ryo);
+    free(tn); free(to); free(kn); free(ko); free(rxn); free(ryn); free(rxo); free(ryo);
+    return count;
+}

@@ -150,6 +150,12 @@ void orc_add_points_mt(orc_map *m, int n, const float *xyzi /* n*4 */, const uns
                        const float T[16], double relLower, double relUpper,
                        const orc_sensor *sensor, const float sJ[3], int nthreads);
 
+/* ElevationMapping::updateGlobalMap (ElevationMapping.cpp:773-905), PARITY UNPINNED: rigid re-transform of a submap and one
+ * pairwise re-fusion (new = the neighbour, old = submap i); points are 8 floats {x,y,z,w,bgra,covariance,intensity,travers};
+ * returns the number of fused cells, clouds compacted in place */
+void orc_transform_cloud(float *pts, int n, const float T[16]);
+int orc_refuse_submaps(float *pn, int *n_new, float *po, int *n_old, double res, int compat);
+
 /* pooled variant of orc_add_points_mt: persistent worker threads, per-band point lists, dynamic band assignment
  * (bench.py's CPU baseline; same results) */
 typedef struct orc_pool orc_pool;

@@ -75,6 +75,9 @@ def load():
     lib.orc_clean_point_cloud.restype = C.c_int
     lib.orc_clean_point_cloud.argtypes = [C.POINTER(OrcSensor), C.c_int, P, P]
     lib.orc_add_points_mt.argtypes = [MP, C.c_int, P, P, P, C.c_double, C.c_double, C.POINTER(OrcSensor), P, C.c_int]
+    lib.orc_transform_cloud.argtypes = [P, C.c_int, P]
+    lib.orc_refuse_submaps.restype = C.c_int
+    lib.orc_refuse_submaps.argtypes = [P, C.POINTER(C.c_int), P, C.POINTER(C.c_int), C.c_double, C.c_int]
     lib.orc_pool_create.restype = P
     lib.orc_pool_create.argtypes = [C.c_int]
     lib.orc_pool_destroy.argtypes = [P]
@@ -97,6 +100,25 @@ def colourise(xyzi, T_camera, T_lidar, bgr):
     rgba = np.zeros((xyzi.shape[0], 4), np.uint8)
     lib.orc_colourise(_p(xyzi), xyzi.shape[0], _p(tc), _p(tl), _p(bgr), bgr.shape[1], bgr.shape[0], 3 * bgr.shape[1], _p(rgba))
     return xyzi, rgba
+
+
+def transform_cloud(pts, T):
+    """oracle twin of gem_transform_cloud on an (n, 8) float32 array (copy)"""
+    lib = load()
+    pts = np.array(pts, np.float32, copy=True, order="C")
+    T = np.ascontiguousarray(T, np.float32).reshape(-1)
+    lib.orc_transform_cloud(_p(pts), pts.shape[0], _p(T))
+    return pts
+
+
+def refuse_submaps(new, old, res, compat=True):
+    """oracle twin of gem_refuse_submaps: returns (new', old', fused)"""
+    lib = load()
+    new = np.array(new, np.float32, copy=True, order="C")
+    old = np.array(old, np.float32, copy=True, order="C")
+    nn, no = C.c_int(new.shape[0]), C.c_int(old.shape[0])
+    fused = lib.orc_refuse_submaps(_p(new), C.byref(nn), _p(old), C.byref(no), float(res), 1 if compat else 0)
+    return new[:nn.value], old[:no.value], fused
 
 
 def sensor_from_frame(frame) -> OrcSensor:

@@ -635,6 +635,60 @@ def test_c5_size_8192_frame_and_multi_sensor_vs_oracle():
     assert np.array_equal(got.view(np.uint32), expect.view(np.uint32)), int((got != expect).sum())
 
 
+def test_loop_closure_submap_refusion_matches_oracle():
+    """SURVEY 8f row 4 (ElevationMapping.cpp:773-905): five overlapping submaps harvested as PointXYZRGBICT records, rigid
+    re-transform + pairwise cell-hash re-fusion on the device vs the oracle twin, both precedence modes; plus the
+    properties that hold at any size: one point per cell afterwards, positions on cell centres, idempotent second pass
+    for cells whose old variance left (0, 1)"""
+    import torch
+    import oracle_lib
+    from gem_b200 import submaps as sm
+    rng = np.random.default_rng(5)
+    res = 0.1
+
+    class OracleBackend:
+        def transform_cloud(self, pts, T):
+            pts[:] = oracle_lib.transform_cloud(pts, T)
+
+        def refuse_submaps(self, new, old, resolution, compat):
+            n2, o2, fused = oracle_lib.refuse_submaps(new, old, resolution, compat)
+            new[:n2.shape[0]] = n2
+            old[:o2.shape[0]] = o2
+            return n2.shape[0], o2.shape[0], fused
+
+    def make_submap(cx, cy, n):
+        p = np.zeros((n, 8), np.float32)
+        p[:, 0] = cx + rng.uniform(-6, 6, n); p[:, 1] = cy + rng.uniform(-6, 6, n)
+        p[:, 2] = rng.uniform(-1, 1, n); p[:, 3] = 1.0
+        p[:, 4] = rng.integers(1, 1 << 24, n).astype(np.uint32).view(np.float32)
+        p[:, 5] = rng.choice([0.05, 0.3, 0.9, 1.2, 0.0, -0.1], n).astype(np.float32)
+        p[:, 6] = rng.integers(1, 255, n); p[:, 7] = rng.uniform(0, 1, n)
+        p[rng.integers(0, n, 5), 0] = np.nan          # a few broken points: they equal nothing and are kept
+        return p
+    centres = [(0.0, 0.0), (4.0, 1.0), (-3.0, 2.0), (2.0, -5.0), (60.0, 60.0)]   # the last one has no neighbour
+    base = [make_submap(cx, cy, 40000) for cx, cy in centres]
+    yaw = lambda a, x, y: np.array([[np.cos(a), -np.sin(a), 0, x], [np.sin(a), np.cos(a), 0, y], [0, 0, 1, 0.02], [0, 0, 0, 1]], np.float32)
+    old_poses = [yaw(0.1 * k, c[0], c[1]) for k, c in enumerate(centres)]
+    new_poses = [yaw(0.1 * k + 0.01, c[0] + 0.07, c[1] - 0.04) for k, c in enumerate(centres)]
+    g = gem_b200.ElevationMap(64, 0.1, compat_box_filter=False)
+    for compat in (True, False):
+        ora = [b.copy() for b in base]
+        dev = [torch.from_numpy(b.copy()).cuda() for b in base]
+        ora, fo = sm.update_global_map(OracleBackend(), ora, old_poses, new_poses, centres, res, 25.0, compat)
+        dev, fd = sm.update_global_map(g, dev, old_poses, new_poses, centres, res, 25.0, compat)
+        assert fo == fd and fo > 1000
+        for k in range(len(base)):
+            a, b = dev[k].cpu().numpy(), ora[k]
+            assert a.shape == b.shape, (k, a.shape, b.shape)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (compat, k, int((a.view(np.uint32) != b.view(np.uint32)).sum()))
+        k0 = dev[0].cpu().numpy()
+        ok = ~np.isnan(k0[:, 0])
+        cells = np.round((k0[ok, :2] + res / 2) / res).astype(np.int64)
+        assert np.unique(cells, axis=0).shape[0] == cells.shape[0]                 # one point per cell
+        assert np.abs((k0[ok, :2] + res / 2) / res - cells).max() < 1e-3           # on cell centres
+        assert base[4].shape[0] == dev[4].shape[0]                                  # no neighbour: untouched (not even hashed)
+
+
 def test_error_paths_return_codes():
     import ctypes as C
     from gem_b200 import _lib

@@ -382,3 +382,30 @@ def test_clean_point_cloud_kats():
         cutoff_min_depth=sys.float_info.min, cutoff_max_depth=sys.float_info.max))
     x, _ = o.clean_point_cloud(pts, None, dflt)
     assert x[:, 3].tolist() == [1, 2, 5, 6, 8]
+
+
+def test_submap_refusion_kats():
+    """ElevationMapping::updateGlobalMap's pairwise loop (ElevationMapping.cpp:847-870) on hand-made submaps: the first
+    point of a cell wins, only cells of the old map with variance in (0, 1) fuse, the fused cell lands in both maps with
+    the new map's colour, positions become cell centres, and the reference's expression parses as it parses"""
+    import oracle_lib
+    res = 0.1
+    def pt(x, y, z, var, col=1, inten=5.0, trav=0.5):
+        return [x, y, z, 1.0, np.float32(np.uint32(col).view(np.float32)), var, inten, trav]
+    new = np.array([pt(0.03, 0.04, 1.0, 0.2, col=11), pt(0.05, 0.06, 9.0, 0.3, col=12),     # same cell: the second is dropped
+                    pt(1.03, 0.04, 2.0, 0.5, col=13), pt(5.0, 5.0, 3.0, 0.1, col=14)], np.float32)
+    old = np.array([pt(0.09, 0.01, 4.0, 0.4, col=21), pt(1.01, 0.09, 5.0, 1.5, col=22),     # variance >= 1: not fused
+                    pt(-3.0, 2.0, 6.0, 0.2, col=23)], np.float32)
+    n2, o2, fused = oracle_lib.refuse_submaps(new, old, res, compat=True)
+    assert fused == 1 and n2.shape[0] == 3 and o2.shape[0] == 3
+    vn2, vo2 = np.float64(np.float32(0.2)) ** 2, np.float64(np.float32(0.4)) ** 2
+    e = np.float32(vn2 * 4.0 + vo2 * 1.0 / vo2 + vn2)      # C precedence: a*b + (c*d)/e + f
+    v = np.float32(vo2 * vn2 / vo2 + vn2)
+    assert n2[0, 2] == e and n2[0, 5] == v and o2[0, 2] == e and o2[0, 5] == v
+    assert o2[0, 4].view(np.uint32) == 11                                        # the new map's colour in both
+    assert np.allclose(n2[0, :2], [0.05, 0.05]) and np.allclose(o2[1, :2], [1.05, 0.05]) and o2[1, 2] == 5.0
+    n3, o3, fused = oracle_lib.refuse_submaps(new, old, res, compat=False)
+    assert fused == 1 and n3[0, 2] == np.float32((vn2 * 4.0 + vo2 * 1.0) / (vo2 + vn2)) and n3[0, 5] == np.float32(vo2 * vn2 / (vo2 + vn2))
+    T = np.array([[0, -1, 0, 1], [1, 0, 0, 2], [0, 0, 1, 3], [0, 0, 0, 1]], np.float32)
+    t = oracle_lib.transform_cloud(new, T)
+    assert np.allclose(t[0, :3], [-0.04 + 1, 0.03 + 2, 1.0 + 3]) and np.array_equal(t[:, 3:], new[:, 3:])
