@@ -582,7 +582,10 @@ __device__ __forceinline__ int fold_small_cell(const MapGeom &g, const MapLayers
     uint4 rr[CHUNK0];
 #pragma unroll
     for (int e = 0; e < 4; e++) rr[e] = c0[e];
-    if (k > CHUNK0) return 0; // folded by a warp (fold_cell_warp)
+    // k > 8: folded by a warp (fold_cell_warp).  k == 0: that warp (or k_fold_long, which may run concurrently) has already
+    // folded the cell and reset its counter -- a cell with a FIRST mark has at least one record until its owner resets it.
+    // Either way the cell is not this thread's: it must not even rewrite the state it loaded.
+    if (k > CHUNK0 || k == 0) return 0;
 #pragma unroll
     for (int e = 4; e < CHUNK0; e++) {
         rr[e] = make_uint4(0u, 0u, 0u, 0u);
@@ -837,7 +840,8 @@ __device__ __noinline__ int fold_cell_warp(const MapGeom &g, const MapLayers &ml
     const int k = ml.cell[key].bin[sc.par].x;
     CellState s;
     cell_begin(s, g, ml, key, do_lowest);
-    if (!from_long && k > FOLD_LONG_FROM) return 0; // the cell also reached rank 40: it is in k_fold_long's queue
+    // a LARGE mark whose cell also reached rank 40 is k_fold_long's; its counter reads > 40, or 0 once that kernel is done with it
+    if (!from_long && (k > FOLD_LONG_FROM || k == 0)) return 0;
     if (k > 0) stamp_since(sc, 3, t0); // list length arrived
     if (k > level_base(3)) c.p[3] = next_chunk(sc.pool + c.p[2]);
     if (k > level_base(4)) c.p[4] = next_chunk(sc.pool + c.p[3]);

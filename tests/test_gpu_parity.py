@@ -680,7 +680,9 @@ def test_loop_closure_submap_refusion_matches_oracle():
         for k in range(len(base)):
             a, b = dev[k].cpu().numpy(), ora[k]
             assert a.shape == b.shape, (k, a.shape, b.shape)
-            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (compat, k, int((a.view(np.uint32) != b.view(np.uint32)).sum()))
+            same = a.view(np.uint32) == b.view(np.uint32)
+            same[:, :3] |= np.isnan(a[:, :3]) & np.isnan(b[:, :3])     # broken points: NaN payload bits differ between x86 and the GPU
+            assert same.all(), (compat, k, int((~same).sum()))
         k0 = dev[0].cpu().numpy()
         ok = ~np.isnan(k0[:, 0])
         cells = np.round((k0[ok, :2] + res / 2) / res).astype(np.int64)

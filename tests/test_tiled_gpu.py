@@ -39,6 +39,7 @@ def test_two_tiles_on_one_gpu_equal_single_map():
         c = torch.from_numpy(frs[r]["rgba"]).to(dev)
         send = torch.zeros((x.shape[0], tiled.REC_WORDS), dtype=torch.int32, device=dev)
         cnt = torch.zeros(world, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
         tiles[r].route_points(x, c, fobj[r], tr, tc, send, cnt)
         tiles[r].sync()
         sends.append(send)
@@ -49,6 +50,7 @@ def test_two_tiles_on_one_gpu_equal_single_map():
             off = sum(counts[src][:dst])
             parts.append(sends[src][off:off + counts[src][dst]])
         recv = torch.cat(parts).contiguous()
+        torch.cuda.synchronize()
         tiles[dst].fuse_records(recv, recv.shape[0])
         tiles[dst].sync()
     total = 0
@@ -94,6 +96,7 @@ def _add_round(single, tiles, world, L, frs, fobj):
         c = torch.from_numpy(frs[r]["rgba"]).to(dev)
         send = torch.zeros((x.shape[0], tiled.REC_WORDS), dtype=torch.int32, device=dev)
         cnt = torch.zeros(world, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
         tiles[r].route_points(x, c, fobj[r], tr, tc, send, cnt)
         tiles[r].sync()
         sends.append(send)
@@ -101,6 +104,7 @@ def _add_round(single, tiles, world, L, frs, fobj):
     for dst in range(world):
         parts = [sends[src][sum(counts[src][:dst]):sum(counts[src][:dst]) + counts[src][dst]] for src in range(world)]
         recv = torch.cat(parts).contiguous()
+        torch.cuda.synchronize()
         tiles[dst].fuse_records(recv, recv.shape[0])
         tiles[dst].sync()
 
