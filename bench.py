@@ -569,6 +569,20 @@ def run_single(args):
         except Exception as e:  # never let a secondary measurement break the headline line
             extra[name] = {"error": repr(e)}
 
+    # ---- the tiled path at world = 1 (what `--gpus N` times, on one GPU): the baseline its scaling curve is read against ----
+    try:
+        import subprocess
+        env = dict(os.environ, GEM_B200_BENCH_PARITY="0", MASTER_ADDR="127.0.0.1")
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1", "--master-addr", "127.0.0.1",
+                            "--master-port", "29677", os.path.abspath(__file__), "--gpus", "2", "--steps", str(min(K, 400)), "--warmup", "10",
+                            "--frames", str(min(F, 32))], capture_output=True, text=True, timeout=240, env=env)
+        tl = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        extra["tiled_path_world1"] = {"value": tl["value"], "unit": "Mpoints/s", "ms_per_step": tl["ms_per_step"],
+                                      "what": "bench.py --gpus N's code path (gem_tiled_step: route + peer bin + fold, pipelined) with one rank that "
+                                              "owns the whole 1024x1024 map; the N-GPU lines divide by N times THIS for the tiled path's own efficiency"}
+    except Exception as e:
+        extra["tiled_path_world1"] = {"error": repr(e)}
+
     # ---- CPU baseline beside it (bounded sample) ----------------------------------------------------
     threads = best_cpu_threads(frames[: min(F, 16)], L, res)
     nb = int(min(max(K, 5), 40))

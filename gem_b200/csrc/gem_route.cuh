@@ -253,9 +253,12 @@ k_route_peer(MapGeom g, FrameParams f, const float4 *xyzi, const uchar4 *rgba, i
         for (int ww = 0; ww < ROUTE_BLOCK / 32; ww++) tot += s_wcnt[ww][threadIdx.x];
         reinterpret_cast<int *>(pb.cnt[threadIdx.x])[(size_t)buf * world * nblk + sub] = tot;
     }
-    __threadfence_system(); // this thread's peer stores are ordered before the flag below
+    // The block's peer stores happen-before thread 0's fence through the barrier (fences are cumulative in the PTX memory
+    // model), and that system-scope fence orders them before the ticket and, in the last block, before the flags: one
+    // fence per block instead of one per thread (which cost half of this kernel's time).
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const int t = atomicAdd(ticket, 1);
         if (t == (int)gridDim.x - 1) { // last block of this rank: everything is on its way -> raise the flag on every peer
             *ticket = 0;
