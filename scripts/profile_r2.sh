@@ -7,9 +7,8 @@ O=gpurun_out
 # 1. launch list of the c2 add loop (serial schedule: plain gem_add_points)
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file $O/r2_launches.csv python scripts/add_loop.py 60 plain > /dev/null 2>&1
 # 2. the three add kernels, full set with source
-for k in k_bin k_fold_long "k_fold\("; do
-  n=$(echo $k | tr -d '\\(')
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:"$k" -s 20 -c 2 -f -o $O/r2_$n python scripts/add_loop.py 30 plain > /dev/null 2>&1
+for k in k_bin k_fold_long k_fold; do   # regex anchored at both ends: "k_fold" must not match k_fold_long
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:"^$k\$" -s 20 -c 2 -f -o $O/r2_$k python scripts/add_loop.py 30 plain > /dev/null 2>&1
 done
 # 3. the 1 M-point batch (gem_add_points_multi into 8192^2): DRAM bytes per launch
 timeout 400 ncu --set full --clock-control none -k regex:"k_bin|k_fold" -s 36 -c 6 -f -o $O/r2_batch python scripts/batch_bench.py 20 > /dev/null 2>&1
