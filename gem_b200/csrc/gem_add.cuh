@@ -837,6 +837,14 @@ __device__ __noinline__ int fold_cell_warp(const MapGeom &g, const MapLayers &ml
     ChunkRefs c;
     c.key = key; c.i8 = info.z; c.p[0] = 0; c.p[1] = 0; c.p[2] = info.w; c.p[3] = 0; c.p[4] = 0;
     const unsigned long long t0 = (sc.stamps && from_long) ? globaltimer_ns() : 0ull;
+    // k_fold (lists of 9..40): where the 40 slots are follows from the mark alone (chunk0 by key, the second chunk by the
+    // index of the rank-8 point), so they are requested together with the cell instead of one round trip later; the slots
+    // beyond the list length hold stale bits and are masked once the length has arrived
+    uint4 spec0 = make_uint4(0u, 0u, 0u, 0u), spec1 = spec0;
+    if (ROWS == 2) {
+        spec0 = *record_ptr(sc, c, (int)lane);
+        if (lane < (unsigned)(FOLD_LONG_FROM - 32)) spec1 = *record_ptr(sc, c, (int)lane + 32);
+    }
     const int k = ml.cell[key].bin[sc.par].x;
     CellState s;
     cell_begin(s, g, ml, key, do_lowest);
@@ -855,7 +863,7 @@ __device__ __noinline__ int fold_cell_warp(const MapGeom &g, const MapLayers &ml
         for (int r = 0; r < ROWS; r++) { // all record loads first ...
             const int e = (int)lane + 32 * r;
             rec[r] = make_uint4(0x7fffffffu, 0u, 0u, 0u); // index padding: never smaller than a real index
-            if (r < rows && e < k) rec[r] = *record_ptr(sc, c, e);
+            if (r < rows && e < k) rec[r] = (ROWS == 2) ? (r == 0 ? spec0 : spec1) : *record_ptr(sc, c, e);
         }
         float it[ROWS];
 #pragma unroll

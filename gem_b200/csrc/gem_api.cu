@@ -51,6 +51,8 @@ struct TiledState { // gem_tiled_attach
     PeerBufs pb{};
     int *d_ticket = nullptr, *d_ntotal = nullptr; // [1], [2] (by call parity)
     int step = 0;
+    int depth = 3;                                 // 3: {route j || bin j-1 || fold j-2} per call; 2: {route j -> bin j || fold j-1}
+    struct { bool active = false; int step = 0, buf = 0; } routed; // depth 3: delivered to the owners, not binned yet
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     cudaGraphNode_t long_node = nullptr, fold_node = nullptr, route_node = nullptr, bin_node = nullptr;
@@ -299,15 +301,72 @@ int launch_fold(gem_map *m, cudaStream_t st, const PendingFold &p, const RegionO
     return GEM_OK;
 }
 
+// the bin kernel of a routed tiled step: its arguments and the fold it leaves behind; takes the call's scratch set
+struct TiledBin {
+    MapGeom gl;
+    MapLayers ml;
+    BinScratch sc;
+    const uint4 *rec;
+    const float *inten;
+    const int *cnt, *flags;
+    int nsub, world, step;
+    int *ntotal;
+    PendingFold fold;
+};
+
+TiledBin tiled_bin_of(gem_map *m, int step, int buf)
+{
+    TiledState &ts = m->tiled;
+    const int par = (int)(m->call_no & 1u), c = (int)(m->call_no % 3u);
+    TiledBin b{};
+    b.gl = m->geom;
+    b.ml = m->ml;
+    b.sc = m->bs[par];
+    b.sc.ctr = m->ctr[c];
+    b.sc.ctr_next = m->ctr[(c + 1) % 3];
+    b.sc.par = par;
+    b.sc.stamps = nullptr;
+    b.world = ts.world;
+    b.nsub = ts.world * ts.nblk;
+    b.step = step;
+    b.rec = (const uint4 *)ts.pb.rec[ts.my_rank] + (size_t)buf * ts.world * ts.cap;
+    b.inten = (const float *)ts.pb.inten[ts.my_rank] + (size_t)buf * ts.world * ts.cap;
+    b.cnt = (const int *)ts.pb.cnt[ts.my_rank] + (size_t)buf * b.nsub;
+    b.flags = (const int *)ts.pb.flag[ts.my_rank];
+    b.ntotal = ts.d_ntotal + par;
+    b.fold.active = true;
+    b.fold.sc = b.sc;
+    b.fold.geom = m->geom;
+    b.fold.n = ts.world * ts.cap;
+    b.fold.n_dev = b.ntotal;
+    b.fold.src = FoldSrc{(const char *)b.inten, 4};
+    m->ctr_last = b.sc.ctr;
+    m->call_no++;
+    return b;
+}
+
+int launch_tiled_bin(gem_map *m, const TiledBin &b)
+{
+    GEM_LAUNCH(m, GEM_PROF_BIN, k_bin_peer<<<b.nsub, ROUTE_BLOCK, 0, m->stream>>>(b.gl, b.ml, b.sc, b.rec, b.inten, b.cnt, b.nsub, b.flags, b.world, b.step, b.ntotal));
+    GEM_CUDA(m, cudaGetLastError());
+    return GEM_OK;
+}
+
 int drain(gem_map *m)
 {
-    if (!m->pend.active) return GEM_OK;
-    if (m->pipe_mode == 1) GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_bin[m->pend.sc.par], 0));
     RegionOps none{};
-    int rc = launch_fold(m, m->stream, m->pend, none, 0, true, true);
-    if (rc) return rc;
-    if (m->pipe_mode == 1) GEM_CUDA(m, cudaEventRecord(m->ev_fold[m->pend.sc.par], m->stream));
-    m->pend.active = false;
+    int rc;
+    if (m->pend.active) {
+        if (m->pipe_mode == 1) GEM_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_bin[m->pend.sc.par], 0));
+        if ((rc = launch_fold(m, m->stream, m->pend, none, 0, true, true))) return rc;
+        if (m->pipe_mode == 1) GEM_CUDA(m, cudaEventRecord(m->ev_fold[m->pend.sc.par], m->stream));
+        m->pend.active = false;
+    }
+    if (m->tiled.routed.active) { // a tiled step that is routed but not binned: bin it, fold it
+        const TiledBin b = tiled_bin_of(m, m->tiled.routed.step, m->tiled.routed.buf);
+        m->tiled.routed.active = false;
+        if ((rc = launch_tiled_bin(m, b)) || (rc = launch_fold(m, m->stream, b.fold, none, 0, true, true))) return rc;
+    }
     return GEM_OK;
 }
 
@@ -1742,14 +1801,18 @@ int gem_tiled_attach(gem_map *m, const gem_tiled_peers *p)
     ts.d_ntotal = ts.d_ticket + 1;
     GEM_CUDA(m, cudaMemsetAsync(ts.d_ticket, 0, 4 * sizeof(int), m->stream));
     ts.step = 0;
+    ts.routed.active = false;
+    if (const char *e = getenv("GEM_B200_TILED_DEPTH")) ts.depth = (atoi(e) == 2) ? 2 : 3;
+    if (ts.exec) { cudaGraphExecDestroy(ts.exec); cudaGraphDestroy(ts.graph); ts.exec = nullptr; ts.graph = nullptr; }
     ts.attached = true;
     return GEM_OK;
 }
 
 // One step of a tiled map: route this rank's cloud to the owning tiles (peer stores), bin what the peers delivered,
-// fold.  Pipelined like gem_add_points_stream: the step issues ONE graph {fold_long, fold of the previous step ||
-// route -> bin of this step}; the fold of the last step is issued by whatever reads the map next (gem_flush).
-// Every rank must make the same sequence of gem_tiled_step calls (a step waits for every peer's flag of that step).
+// fold.  Pipelined three deep: call j issues ONE graph with four independent kernels {fold_long, fold of step j-2 || bin
+// of step j-1 || route of step j}; what is outstanding after the last call is issued by whatever reads the map next
+// (gem_flush).  Every rank must make the same sequence of gem_tiled_step calls (a bin waits for every peer's flag of
+// its step).  GEM_B200_TILED_DEPTH=2: {fold_long, fold of step j-1 || route -> bin of step j}.
 int gem_tiled_step(gem_map *m, const void *xyzi, const void *rgba, int n, const gem_frame *frame)
 {
     if (!m || !frame || n < 0 || (n > 0 && !xyzi)) return fail(m, GEM_ERR_INVALID, "gem_tiled_step: bad argument");
@@ -1765,77 +1828,80 @@ int gem_tiled_step(gem_map *m, const void *xyzi, const void *rgba, int n, const 
         if ((rc = drain(m)) || (rc = flush_all_pending(m))) return rc;
     }
     ts.step++;
-    const int step = ts.step, buf = step % 3, world = ts.world, nsub = world * ts.nblk;
-    const int par = (int)(m->call_no & 1u), c = (int)(m->call_no % 3u);
-    BinScratch sc = m->bs[par];
-    sc.ctr = m->ctr[c];
-    sc.ctr_next = m->ctr[(c + 1) % 3];
-    sc.par = par;
-    sc.stamps = nullptr;
-    MapGeom gg = m->geom, gl = m->geom;
+    const int world = ts.world;
+    MapGeom gg = m->geom;
     gg.tiled = 0; // routing works on global geographic indices
     FrameParams fp = make_frame(frame);
-    const int tile_h = (m->L + ts.tiles_r - 1) / ts.tiles_r, tile_w = (m->L + ts.tiles_c - 1) / ts.tiles_c;
+    int th = (m->L + ts.tiles_r - 1) / ts.tiles_r, tw = (m->L + ts.tiles_c - 1) / ts.tiles_c;
     const float4 *px = (const float4 *)xyzi;
     const uchar4 *pr = (const uchar4 *)rgba;
-    int nn = n, tiles_c = ts.tiles_c, my_rank = ts.my_rank, nblk = ts.nblk, cap = ts.cap, bufv = buf, stepv = step, worldv = world, nsubv = nsub;
-    int *ticket = ts.d_ticket, *ntotal = ts.d_ntotal + par;
+    int nn = n, tiles_c = ts.tiles_c, my_rank = ts.my_rank, nblk = ts.nblk, cap = ts.cap, bufv = ts.step % PEER_BUFS, stepv = ts.step, worldv = world;
+    int *ticket = ts.d_ticket;
     PeerBufs pb = ts.pb;
-    const uint4 *my_rec = (const uint4 *)pb.rec[my_rank] + (size_t)buf * world * cap;
-    const float *my_int = (const float *)pb.inten[my_rank] + (size_t)buf * world * cap;
-    const int *my_cnt = (const int *)pb.cnt[my_rank] + (size_t)buf * nsub;
-    const int *my_flags = (const int *)pb.flag[my_rank];
-    MapLayers ml = m->ml;
-    int th = tile_h, tw = tile_w;
     void *route_args[] = {&gg, &fp, &px, &pr, &nn, &th, &tw, &tiles_c, &worldv, &my_rank, &nblk, &cap, &bufv, &stepv, &pb, &ticket};
-    void *bin_args[] = {&gl, &ml, &sc, &my_rec, &my_int, &my_cnt, &nsubv, &my_flags, &worldv, &stepv, &ntotal};
-    PendingFold cur;
-    cur.active = true; cur.sc = sc; cur.geom = m->geom; cur.n = world * cap; cur.n_dev = ntotal;
-    cur.src = FoldSrc{(const char *)my_int, 4};
-    if (serial || !m->pend.active || m->pipe_mode != 2) {
-        if ((rc = drain(m))) return rc;
+    auto launch_route = [&]() -> int {
         GEM_LAUNCH(m, GEM_PROF_ROUTE, k_route_peer<<<nblk, ROUTE_BLOCK, 0, m->stream>>>(gg, fp, px, pr, nn, th, tw, tiles_c, worldv, my_rank, nblk, cap, bufv, stepv, pb, ticket));
-        GEM_LAUNCH(m, GEM_PROF_BIN, k_bin_peer<<<nsub, ROUTE_BLOCK, 0, m->stream>>>(gl, ml, sc, my_rec, my_int, my_cnt, nsubv, my_flags, worldv, stepv, ntotal));
         GEM_CUDA(m, cudaGetLastError());
-        if (serial) {
-            RegionOps none{};
-            if ((rc = launch_fold(m, m->stream, cur, none, 0, true, true))) return rc;
-        } else {
-            m->pend = cur;
-        }
-    } else {
-        PendingFold prev = m->pend;
-        const int fb = fold_blocks_for(m, prev.n);
-        int slice = fold_slice(prev.n, fb), fbk = fb, one = 1;
-        RegionOps none{};
-        void *fold_args[] = {&prev.geom, &ml, &prev.sc, &prev.src, &none, &prev.n, &fbk, &slice, &one, &one, (void *)&prev.n_dev};
-        void *long_args[] = {&prev.geom, &ml, &prev.sc, &prev.src, &none, &one, &one};
-        cudaKernelNodeParams kl{}, kf{}, kr{}, kb{};
-        kl.func = (void *)k_fold_long; kl.gridDim = dim3((unsigned)long_blocks_for(m, prev.n / world)); kl.blockDim = dim3(LONG_BLOCK); kl.sharedMemBytes = (unsigned)m->long_smem; kl.kernelParams = long_args;
-        kf.func = (void *)k_fold; kf.gridDim = dim3((unsigned)fb); kf.blockDim = dim3(ADD_BLOCK); kf.sharedMemBytes = (unsigned)m->fold_smem; kf.kernelParams = fold_args;
-        kr.func = (void *)k_route_peer; kr.gridDim = dim3((unsigned)nblk); kr.blockDim = dim3(ROUTE_BLOCK); kr.sharedMemBytes = 0; kr.kernelParams = route_args;
-        kb.func = (void *)k_bin_peer; kb.gridDim = dim3((unsigned)nsub); kb.blockDim = dim3(ROUTE_BLOCK); kb.sharedMemBytes = 0; kb.kernelParams = bin_args;
-        if (!ts.exec) {
-            GEM_CUDA(m, cudaGraphCreate(&ts.graph, 0));
-            GEM_CUDA(m, cudaGraphAddKernelNode(&ts.long_node, ts.graph, nullptr, 0, &kl));
-            GEM_CUDA(m, cudaGraphAddKernelNode(&ts.route_node, ts.graph, nullptr, 0, &kr));
-            GEM_CUDA(m, cudaGraphAddKernelNode(&ts.fold_node, ts.graph, nullptr, 0, &kf));
-            GEM_CUDA(m, cudaGraphAddKernelNode(&ts.bin_node, ts.graph, &ts.route_node, 1, &kb));
-            GEM_CUDA(m, cudaGraphInstantiate(&ts.exec, ts.graph, 0));
-        } else {
-            GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.long_node, &kl));
-            GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.route_node, &kr));
-            GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.fold_node, &kf));
-            GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.bin_node, &kb));
-        }
-        GEM_CUDA(m, cudaGraphLaunch(ts.exec, m->stream));
-        m->launches += 4;
-        m->pend = cur;
-    }
-    m->ctr_last = sc.ctr;
-    m->call_no++;
+        return GEM_OK;
+    };
     memset(&m->stats, 0, sizeof m->stats);
     m->stats.points_in = n;
+    RegionOps none{};
+    int one = 1;
+    const bool graphs = !serial && m->pipe_mode == 2;
+    if (!graphs || ts.depth == 2) {
+        // route -> bin of this step on the stream or in one graph with the previous step's folds
+        if (!graphs || !m->pend.active) {
+            if ((rc = drain(m)) || (rc = launch_route())) return rc;
+            const TiledBin b = tiled_bin_of(m, stepv, bufv);
+            if ((rc = launch_tiled_bin(m, b))) return rc;
+            if (serial) return launch_fold(m, m->stream, b.fold, none, 0, true, true);
+            m->pend = b.fold;
+            return GEM_OK;
+        }
+    } else if (!ts.routed.active || !m->pend.active) {
+        // depth 3, pipeline filling (first two calls, or after a flush): plain launches, one after the other
+        if (!ts.routed.active) {
+            if ((rc = drain(m)) || (rc = launch_route())) return rc;
+        } else {
+            const TiledBin b = tiled_bin_of(m, ts.routed.step, ts.routed.buf);
+            if ((rc = launch_tiled_bin(m, b)) || (rc = launch_route())) return rc;
+            m->pend = b.fold;
+        }
+        ts.routed.active = true; ts.routed.step = stepv; ts.routed.buf = bufv;
+        return GEM_OK;
+    }
+    // steady state: one graph
+    PendingFold prev = m->pend;
+    TiledBin b = (ts.depth == 2) ? tiled_bin_of(m, stepv, bufv) : tiled_bin_of(m, ts.routed.step, ts.routed.buf);
+    const int fb = fold_blocks_for(m, prev.n);
+    int slice = fold_slice(prev.n, fb), fbk = fb;
+    void *fold_args[] = {&prev.geom, &b.ml, &prev.sc, &prev.src, &none, &prev.n, &fbk, &slice, &one, &one, (void *)&prev.n_dev};
+    void *long_args[] = {&prev.geom, &b.ml, &prev.sc, &prev.src, &none, &one, &one};
+    void *bin_args[] = {&b.gl, &b.ml, &b.sc, &b.rec, &b.inten, &b.cnt, &b.nsub, &b.flags, &b.world, &b.step, &b.ntotal};
+    cudaKernelNodeParams kl{}, kf{}, kr{}, kb{};
+    kl.func = (void *)k_fold_long; kl.gridDim = dim3((unsigned)long_blocks_for(m, prev.n / world)); kl.blockDim = dim3(LONG_BLOCK); kl.sharedMemBytes = (unsigned)m->long_smem; kl.kernelParams = long_args;
+    kf.func = (void *)k_fold; kf.gridDim = dim3((unsigned)fb); kf.blockDim = dim3(ADD_BLOCK); kf.sharedMemBytes = (unsigned)m->fold_smem; kf.kernelParams = fold_args;
+    kr.func = (void *)k_route_peer; kr.gridDim = dim3((unsigned)nblk); kr.blockDim = dim3(ROUTE_BLOCK); kr.sharedMemBytes = 0; kr.kernelParams = route_args;
+    kb.func = (void *)k_bin_peer; kb.gridDim = dim3((unsigned)b.nsub); kb.blockDim = dim3(ROUTE_BLOCK); kb.sharedMemBytes = 0; kb.kernelParams = bin_args;
+    if (!ts.exec) {
+        GEM_CUDA(m, cudaGraphCreate(&ts.graph, 0));
+        GEM_CUDA(m, cudaGraphAddKernelNode(&ts.long_node, ts.graph, nullptr, 0, &kl));
+        GEM_CUDA(m, cudaGraphAddKernelNode(&ts.route_node, ts.graph, nullptr, 0, &kr));
+        GEM_CUDA(m, cudaGraphAddKernelNode(&ts.fold_node, ts.graph, nullptr, 0, &kf));
+        if (ts.depth == 2) GEM_CUDA(m, cudaGraphAddKernelNode(&ts.bin_node, ts.graph, &ts.route_node, 1, &kb));
+        else GEM_CUDA(m, cudaGraphAddKernelNode(&ts.bin_node, ts.graph, nullptr, 0, &kb));
+        GEM_CUDA(m, cudaGraphInstantiate(&ts.exec, ts.graph, 0));
+    } else {
+        GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.long_node, &kl));
+        GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.route_node, &kr));
+        GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.fold_node, &kf));
+        GEM_CUDA(m, cudaGraphExecKernelNodeSetParams(ts.exec, ts.bin_node, &kb));
+    }
+    GEM_CUDA(m, cudaGraphLaunch(ts.exec, m->stream));
+    m->launches += 4;
+    m->pend = b.fold;
+    if (ts.depth != 2) { ts.routed.active = true; ts.routed.step = stepv; ts.routed.buf = bufv; }
     return GEM_OK;
 }
 

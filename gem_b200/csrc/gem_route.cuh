@@ -201,15 +201,19 @@ inline cudaError_t route_points(cudaStream_t st, const MapGeom &g, const FramePa
 // slot index that the fold sorts a cell's records by -- so the tiled map equals the single-GPU map of the rank-by-rank
 // concatenated clouds bit for bit, although the buffer has holes.  The work list (marks) is dense: a sub-bucket's marks
 // start at the sum of the counts in front of it.
-// Receive buffers are triple-buffered by step: the fold of step i-1 (issued with step i) still reads intensities from
-// buffer (i-1) % 3 while the peers of step i write buffer i % 3; buffer (i+2) % 3 = (i-1) % 3 is written in step i+2,
-// which no peer can reach before this rank has raised its flag of step i+1, i.e. after its graph of step i (with that
-// fold) has completed.
+// Steps are pipelined three deep: the graph of call j runs {route of step j || bin of step j-1 || folds of step j-2}, so
+// the flags a bin kernel waits for were raised one whole graph earlier (no rank waits for a peer unless that peer is a
+// full step behind) and route -> bin is not a dependent chain inside a step.
+// Receive buffers: PEER_BUFS = 5 by step.  Peer p's route of step k+5 rewrites this rank's buffer k % 5, which this rank's
+// fold of step k reads (intensities) in its graph k+2.  p's graph k+5 starts after p's graph k+4, whose bin of step k+3
+// waited for this rank's flag k+3, raised by this rank's route in ITS graph k+3, which started after its graph k+2 had
+// completed.  (Four buffers would not do: flag k+2 is raised inside the very graph k+2 that still folds step k.)
 // =========================================================================================
+constexpr int PEER_BUFS = 5;
 struct PeerBufs { // device addresses valid on THIS device (own memory or peer mappings), per rank
-    unsigned long long rec[ROUTE_MAX_OWNERS];   // uint4 [3][world * cap]  {gkey, h, var, rgb}
-    unsigned long long inten[ROUTE_MAX_OWNERS]; // float [3][world * cap]
-    unsigned long long cnt[ROUTE_MAX_OWNERS];   // int   [3][world * nblk]
+    unsigned long long rec[ROUTE_MAX_OWNERS];   // uint4 [PEER_BUFS][world * cap]  {gkey, h, var, rgb}
+    unsigned long long inten[ROUTE_MAX_OWNERS]; // float [PEER_BUFS][world * cap]
+    unsigned long long cnt[ROUTE_MAX_OWNERS];   // int   [PEER_BUFS][world * nblk]
     unsigned long long flag[ROUTE_MAX_OWNERS];  // int   [world]: flag[o][r] = last step rank r has delivered to rank o
 };
 

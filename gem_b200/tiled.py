@@ -155,9 +155,9 @@ class TiledElevationMap:
             self.cap = nblk * 256
             grp = dist.group.WORLD.group_name
             with torch.cuda.stream(self.stream):
-                self.p_rec = symm_mem.empty((3, self.world * self.cap, 4), dtype=torch.int32, device=self.dev)
-                self.p_int = symm_mem.empty((3, self.world * self.cap), dtype=torch.float32, device=self.dev)
-                self.p_cnt = symm_mem.empty((3, self.world * nblk), dtype=torch.int32, device=self.dev)
+                self.p_rec = symm_mem.empty((5, self.world * self.cap, 4), dtype=torch.int32, device=self.dev)
+                self.p_int = symm_mem.empty((5, self.world * self.cap), dtype=torch.float32, device=self.dev)
+                self.p_cnt = symm_mem.empty((5, self.world * nblk), dtype=torch.int32, device=self.dev)
                 self.p_flag = symm_mem.empty((64,), dtype=torch.int32, device=self.dev)
                 self.p_cnt.zero_()
                 self.p_flag.zero_()
@@ -242,7 +242,7 @@ class TiledElevationMap:
         return self.map.get_layer(name)
 
 
-def parity_check(mode: str = "peer", steps: int = 3, L_per_rank: int = 512, res: float = 0.1, with_cleanup: bool = True):
+def parity_check(mode: str = "peer", steps: int = 7, L_per_rank: int = 512, res: float = 0.1, with_cleanup: bool = True):
     """N ranks build a tiled map and compare it with the untiled map that rank 0 computes alone on the same clouds
     (gem_add_points_multi of the rank-by-rank concatenated clouds), bit for bit, layer by layer.  Collective: every
     rank of the default process group must call it.  Returns {"status", "mismatching_cells", "cells_checked",

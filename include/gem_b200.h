@@ -354,17 +354,20 @@ int gem_refuse_submaps(gem_map *m, void *new_points32_device, int *n_new, void *
 /* ---- tiled maps, peer path: one kernel routes AND exchanges (no collective library, no barrier kernel) ----------
  * The caller allocates, on every rank, four peer-accessible buffers (e.g. CUDA IPC / torch symmetric memory; the
  * library does no inter-process plumbing) and passes the addresses under which THIS device sees every rank's copy:
- *   recv_records   uint4 [3][world * cap]   {global geographic key, height, variance, rgb}
- *   recv_intensity float [3][world * cap]
- *   recv_counts    int   [3][world * cap / 256]
+ *   recv_records   uint4 [5][world * cap]   {global geographic key, height, variance, rgb}
+ *   recv_intensity float [5][world * cap]
+ *   recv_counts    int   [5][world * cap / 256]
  *   flags          int   [world], zero-initialised before the first step
  * with cap = bucket_capacity rounded up to a multiple of 256 (>= the largest cloud any rank adds per step; world * cap
  * <= max_points).  gem_tiled_step(r) = transform rank r's cloud, store every in-grid point into the OWNING rank's
  * buffer over NVLink (slot = (r * cap / 256 + source block) * 256 + position in the block: deterministic, source
  * order), raise rank r's flag on every peer; then, once every peer's flag of this step is up, bin and fold what
  * arrived.  The result equals the single-GPU map of the rank-by-rank concatenated clouds bit for bit.  Steps are
- * pipelined like gem_add_points_stream (gem_flush / gem_sync / any reading call issues the last fold); every rank
- * must make the same sequence of gem_tiled_step calls. */
+ * pipelined three deep: call j issues ONE graph {route of step j || bin of step j-1 || folds of step j-2}, so the
+ * cloud of a call is consumed by that call's graph, and the map contains a step two calls later or after gem_flush /
+ * gem_sync / any reading call (which issue the outstanding bin and folds).  Every rank must make the same sequence of
+ * gem_tiled_step calls (a bin waits on the device for every peer's flag of its step).  GEM_B200_TILED_DEPTH=2 keeps
+ * route -> bin of the same step in one graph (round-2 first version, for A/B). */
 typedef struct gem_tiled_peers {
     int tiles_r, tiles_c, my_rank, bucket_capacity;
     unsigned long long recv_records[64], recv_intensity[64], recv_counts[64], flags[64];
