@@ -1048,6 +1048,7 @@ k_fold(MapGeom g, MapLayers ml, BinScratch sc, FoldSrc src, const __grid_constan
             wk = max(wk, k);
             wtot += k;
         }
+        stamp_mark(sc, 11); // the block's first warp has no large cell left
         for (;;) { // short lists: 32 per warp and draw, one per thread
             int j = 0;
             if (lane == 0u) j = atomicAdd(&s_next_first, 32);
@@ -1060,6 +1061,7 @@ k_fold(MapGeom g, MapLayers ml, BinScratch sc, FoldSrc src, const __grid_constan
                 tsum += k;
             }
         }
+        stamp_mark(sc, 13); // ... and no short list
         // statistics: points binned, longest list (cells touched = nfirst)
         int tmax = tk;
 #pragma unroll

@@ -51,7 +51,7 @@ struct TiledState { // gem_tiled_attach
     PeerBufs pb{};
     int *d_ticket = nullptr, *d_ntotal = nullptr; // [1], [2] (by call parity)
     int step = 0;
-    int depth = 3;                                 // 3: {route j || bin j-1 || fold j-2} per call; 2: {route j -> bin j || fold j-1}
+    int depth = 2;                                 // 2: {route j -> bin j || fold j-1} per call; 3: {route j || bin j-1 || fold j-2}
     struct { bool active = false; int step = 0, buf = 0; } routed; // depth 3: delivered to the owners, not binned yet
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -1802,7 +1802,7 @@ int gem_tiled_attach(gem_map *m, const gem_tiled_peers *p)
     GEM_CUDA(m, cudaMemsetAsync(ts.d_ticket, 0, 4 * sizeof(int), m->stream));
     ts.step = 0;
     ts.routed.active = false;
-    if (const char *e = getenv("GEM_B200_TILED_DEPTH")) ts.depth = (atoi(e) == 2) ? 2 : 3;
+    if (const char *e = getenv("GEM_B200_TILED_DEPTH")) ts.depth = (atoi(e) == 3) ? 3 : 2;
     if (ts.exec) { cudaGraphExecDestroy(ts.exec); cudaGraphDestroy(ts.graph); ts.exec = nullptr; ts.graph = nullptr; }
     ts.attached = true;
     return GEM_OK;

@@ -257,18 +257,21 @@ k_route_peer(MapGeom g, FrameParams f, const float4 *xyzi, const uchar4 *rgba, i
         for (int ww = 0; ww < ROUTE_BLOCK / 32; ww++) tot += s_wcnt[ww][threadIdx.x];
         reinterpret_cast<int *>(pb.cnt[threadIdx.x])[(size_t)buf * world * nblk + sub] = tot;
     }
-    // The block's peer stores happen-before thread 0's fence through the barrier (fences are cumulative in the PTX memory
-    // model), and that system-scope fence orders them before the ticket and, in the last block, before the flags: one
-    // fence per block instead of one per thread (which cost half of this kernel's time).
+    // Visibility chain (PTX memory model; causality order composes across scopes):
+    //   the block's peer stores -> barrier -> thread 0: fence at GPU scope -> ticket atomic            (every block)
+    //   last block: ticket atomic (observes all others) -> ONE fence at system scope -> flag stores (relaxed.sys: fence + store = release)
+    //   owner: flag load (acquire.sys) -> record loads.
+    // A system-scope fence per block cost 44 % of this kernel's and k_bin_peer's stall samples together (MEMBAR.SYS drains
+    // to every memory the SM could have written; profiles/r2_tiled_world1_kernels_full.txt: 17.4 us), one per thread twice that.
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
         const int t = atomicAdd(ticket, 1);
         if (t == (int)gridDim.x - 1) { // last block of this rank: everything is on its way -> raise the flag on every peer
             *ticket = 0;
-            __threadfence_system();
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
             for (int o = 0; o < world; o++)
-                asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(reinterpret_cast<int *>(pb.flag[o]) + my_rank), "r"(step) : "memory");
+                asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(reinterpret_cast<int *>(pb.flag[o]) + my_rank), "r"(step) : "memory");
         }
     }
 }

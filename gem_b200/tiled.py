@@ -284,7 +284,7 @@ def parity_check(mode: str = "peer", steps: int = 7, L_per_rank: int = 512, res:
     bad = checked = valid = 0
     full = None
     if rank == 0:
-        single = gem_b200.ElevationMap(L, res, compat_box_filter=False)
+        single = gem_b200.ElevationMap(L, res, compat_box_filter=False, max_points=max(1 << 20, world * cap))
         single.move(pos)
         for s in range(steps):          # per step ONE multi-sensor frame: the ranks' clouds in rank order
             cl = [cloud(r, s) for r in range(world)]
