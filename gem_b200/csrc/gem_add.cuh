@@ -46,6 +46,7 @@ struct BinCounters { // one counter per 128-byte line
     int ntouched; int pad3[31];  // statistics, accumulated by the folds: cells touched,
     int total;    int pad4[31];  //   points binned (accepted AND inside the grid / tile),
     int maxk;     int pad5[31];  //   longest per-cell list
+    int nmarks;   int pad6[31];  // tiled maps: marks written by k_bin_peer (the fold's work list length)
 };
 
 // what point i was for its cell: nothing, or the point that drew rank 0 / 8 / 40.  The fold finds its work here.
@@ -337,7 +338,7 @@ __device__ __forceinline__ void bin_points(const MapGeom &g, const FrameParams &
 
 __device__ __forceinline__ void zero_next_counters(const BinScratch &sc, int tid)
 {
-    if (tid < (int)(sizeof(BinCounters) / sizeof(int))) ((int *)sc.ctr_next)[tid] = 0; // 192 ints: the bin grids have >= 256 threads
+    if (tid < (int)(sizeof(BinCounters) / sizeof(int))) ((int *)sc.ctr_next)[tid] = 0; // 224 ints: the bin grids have >= 256 threads
 }
 
 template <int SRC, int U>

@@ -333,7 +333,7 @@ TiledBin tiled_bin_of(gem_map *m, int step, int buf)
     b.inten = (const float *)ts.pb.inten[ts.my_rank] + (size_t)buf * ts.world * ts.cap;
     b.cnt = (const int *)ts.pb.cnt[ts.my_rank] + (size_t)buf * b.nsub;
     b.flags = (const int *)ts.pb.flag[ts.my_rank];
-    b.ntotal = ts.d_ntotal + par;
+    b.ntotal = &b.sc.ctr->nmarks; // zero when the call starts (zeroed by the bin kernel of the call before)
     b.fold.active = true;
     b.fold.sc = b.sc;
     b.fold.geom = m->geom;
@@ -345,9 +345,11 @@ TiledBin tiled_bin_of(gem_map *m, int step, int buf)
     return b;
 }
 
+static int bin_peer_blocks(int nsub) { return nsub < BIN_PEER_MAX_BLOCKS ? nsub : BIN_PEER_MAX_BLOCKS; }
+
 int launch_tiled_bin(gem_map *m, const TiledBin &b)
 {
-    GEM_LAUNCH(m, GEM_PROF_BIN, k_bin_peer<<<b.nsub, ROUTE_BLOCK, 0, m->stream>>>(b.gl, b.ml, b.sc, b.rec, b.inten, b.cnt, b.nsub, b.flags, b.world, b.step, b.ntotal));
+    GEM_LAUNCH(m, GEM_PROF_BIN, k_bin_peer<<<bin_peer_blocks(b.nsub), ROUTE_BLOCK, 0, m->stream>>>(b.gl, b.ml, b.sc, b.rec, b.inten, b.cnt, b.nsub, b.flags, b.world, b.step, b.ntotal));
     GEM_CUDA(m, cudaGetLastError());
     return GEM_OK;
 }
@@ -1883,7 +1885,7 @@ int gem_tiled_step(gem_map *m, const void *xyzi, const void *rgba, int n, const 
     kl.func = (void *)k_fold_long; kl.gridDim = dim3((unsigned)long_blocks_for(m, prev.n / world)); kl.blockDim = dim3(LONG_BLOCK); kl.sharedMemBytes = (unsigned)m->long_smem; kl.kernelParams = long_args;
     kf.func = (void *)k_fold; kf.gridDim = dim3((unsigned)fb); kf.blockDim = dim3(ADD_BLOCK); kf.sharedMemBytes = (unsigned)m->fold_smem; kf.kernelParams = fold_args;
     kr.func = (void *)k_route_peer; kr.gridDim = dim3((unsigned)nblk); kr.blockDim = dim3(ROUTE_BLOCK); kr.sharedMemBytes = 0; kr.kernelParams = route_args;
-    kb.func = (void *)k_bin_peer; kb.gridDim = dim3((unsigned)b.nsub); kb.blockDim = dim3(ROUTE_BLOCK); kb.sharedMemBytes = 0; kb.kernelParams = bin_args;
+    kb.func = (void *)k_bin_peer; kb.gridDim = dim3((unsigned)bin_peer_blocks(b.nsub)); kb.blockDim = dim3(ROUTE_BLOCK); kb.sharedMemBytes = 0; kb.kernelParams = bin_args;
     if (!ts.exec) {
         GEM_CUDA(m, cudaGraphCreate(&ts.graph, 0));
         GEM_CUDA(m, cudaGraphAddKernelNode(&ts.long_node, ts.graph, nullptr, 0, &kl));

@@ -199,8 +199,8 @@ inline cudaError_t route_points(cudaStream_t st, const MapGeom &g, const FramePa
 // Determinism: rank r's block b owns slots [(r * nblk + b) * 256, +256) of every owner's buffer, filled in source
 // order without a cross-block scan.  The slot index is monotone in (source rank, source point index), and it is the
 // slot index that the fold sorts a cell's records by -- so the tiled map equals the single-GPU map of the rank-by-rank
-// concatenated clouds bit for bit, although the buffer has holes.  The work list (marks) is dense: a sub-bucket's marks
-// start at the sum of the counts in front of it.
+// concatenated clouds bit for bit, although the buffer has holes.  The work list (marks) is dense and in no particular
+// order (the fold's result does not depend on which thread folds a cell): a sub-bucket takes its range with one atomic.
 // Steps are pipelined three deep: the graph of call j runs {route of step j || bin of step j-1 || folds of step j-2}, so
 // the flags a bin kernel waits for were raised one whole graph earlier (no rank waits for a peer unless that peer is a
 // full step behind) and route -> bin is not a dependent chain inside a step.
@@ -309,47 +309,45 @@ __device__ __forceinline__ void bin_one(Cell *cells, const BinScratch &sc, int k
     *dst = rec;
 }
 
+constexpr int BIN_PEER_MAX_BLOCKS = 148 * 8; // one wave of 256-thread blocks; a block takes sub-buckets blockIdx.x + q * gridDim.x
+constexpr int BIN_PEER_MAX_PER_BLOCK = 32;
+
 __global__ void __launch_bounds__(ROUTE_BLOCK)
 k_bin_peer(MapGeom g, MapLayers ml, BinScratch sc, const uint4 *rec, const float *inten, const int *cnt, int nsub, const int *flags,
-           int world, int step, int *n_total)
+           int world, int step, int *n_marks)
 {
-    __shared__ int s_red[ROUTE_BLOCK / 32];
+    __shared__ int s_cnt[BIN_PEER_MAX_PER_BLOCK];
     __shared__ int s_base;
-    const int sb = blockIdx.x;
-    if (sb == 0) zero_next_counters(sc, threadIdx.x);
-    if (threadIdx.x == 0) { // all peers have delivered this step (their records, counts and everything before the flag)
-        for (int r = 0; r < world; r++) {
-            int v;
-            do {
-                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
-                if (v < step) __nanosleep(100);
-            } while (v < step);
+    if (blockIdx.x == 0) zero_next_counters(sc, threadIdx.x);
+    if ((int)threadIdx.x < world) { // all peers have delivered this step (their records, counts and everything before the flag):
+        int v;                      // one thread per peer, so the block waits for one round trip, not for `world` of them
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (v < step) __nanosleep(100);
+        } while (v < step);
+    }
+    __syncthreads();
+    const int nmine = (nsub - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x; // <= BIN_PEER_MAX_PER_BLOCK (host)
+    if ((int)threadIdx.x < nmine) s_cnt[threadIdx.x] = cnt[blockIdx.x + threadIdx.x * gridDim.x];
+    __syncthreads();
+    for (int q = 0; q < nmine; q++) {
+        const int c = s_cnt[q];
+        if (c == 0) continue; // most sub-buckets of a large world are empty: a source's points land in few tiles
+        const int sb = blockIdx.x + q * gridDim.x;
+        // the marks are the fold's work list: any order will do as long as [0, *n_marks) is dense, so a sub-bucket takes its
+        // range with one atomic (a few hundred per step) instead of summing the counts in front of it
+        if (threadIdx.x == 0) s_base = atomicAdd(n_marks, c);
+        __syncthreads();
+        if ((int)threadIdx.x < c) {
+            const int slot = sb * ROUTE_BLOCK + threadIdx.x; // monotone in (source rank, source point index): the fold's sort key
+            const uint4 r = rec[slot];
+            const int gkey = (int)r.x;
+            const int gx = gkey / g.L, gy = gkey - gx * g.L;
+            const int key = local_key(g, gx, gy);
+            bin_one(ml.cell, sc, key, g.tiled ? key : gkey, make_uint4((uint32_t)slot, r.y, r.z, with_colour_flag(r.w, inten[slot])), slot, s_base + threadIdx.x);
         }
+        __syncthreads(); // s_base is reused
     }
-    __syncthreads();
-    const int c = cnt[sb];
-    const bool last = sb == nsub - 1;
-    if (c == 0 && !last) return;
-    int part = 0; // dense start of this sub-bucket's marks = sum of the counts in front of it
-    for (int j = threadIdx.x; j < sb; j += ROUTE_BLOCK) part += cnt[j];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-    if ((threadIdx.x & 31u) == 0u) s_red[threadIdx.x >> 5] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int b = 0;
-        for (int ww = 0; ww < ROUTE_BLOCK / 32; ww++) b += s_red[ww];
-        s_base = b;
-        if (last) *n_total = b + c;
-    }
-    __syncthreads();
-    if ((int)threadIdx.x >= c) return;
-    const int slot = sb * ROUTE_BLOCK + threadIdx.x; // monotone in (source rank, source point index): the fold's sort key
-    const uint4 r = rec[slot];
-    const int gkey = (int)r.x;
-    const int gx = gkey / g.L, gy = gkey - gx * g.L;
-    const int key = local_key(g, gx, gy);
-    bin_one(ml.cell, sc, key, g.tiled ? key : gkey, make_uint4((uint32_t)slot, r.y, r.z, with_colour_flag(r.w, inten[slot])), slot, s_base + threadIdx.x);
 }
 
 } // namespace gem
