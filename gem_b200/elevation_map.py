@@ -474,5 +474,11 @@ class ElevationMap:
         if rc:
             check(rc, self._h, "gem_tiled_step")
 
+    def tiled_step_fast(self, xyzi_ptr, rgba_ptr, n: int, frame_ref):
+        """gem_tiled_step with raw device addresses (c_void_p) and a byref'd gem_frame: minimal host time per step"""
+        rc = self._lib.gem_tiled_step(self._h, xyzi_ptr, rgba_ptr, n, frame_ref)
+        if rc:
+            check(rc, self._h, "gem_tiled_step")
+
     def fuse_records(self, rec, n: int):
         check(self._lib.gem_fuse_records(self._h, _ptr(rec), int(n)), self._h, "gem_fuse_records")

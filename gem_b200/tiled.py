@@ -394,11 +394,34 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
         except Exception as e:
             parity = {"status": "ERROR", "error": repr(e)}
 
-    def step(s):
-        k = pingpong(s, F)
-        tm.map.move(pos[k])
-        tm.add(xyzi_d[k], rgba_d[k], fobjs[k])
-        return npts[k]
+    import ctypes as C
+    import time
+    # the peer path makes no torch call per step (the library launches on its own stream), so the step is driven like the
+    # N = 1 bench drives gem_add_points_stream: prebuilt ctypes arguments, no Python wrappers in the loop -- with them the
+    # host needed longer per step than the GPUs (25-30 us against ~22 us at 2 GPUs)
+    xp = [C.c_void_p(t.data_ptr()) for t in xyzi_d]
+    rp = [C.c_void_p(t.data_ptr()) for t in rgba_d]
+    posc = [(C.c_float * 3)(*[float(v) for v in p]) for p in pos]
+
+    def make_step(fo):
+        if not tm.peer:
+            def step(s):
+                k = pingpong(s, F)
+                tm.map.move_fast(posc[k])
+                tm.add(xyzi_d[k], rgba_d[k], fo[k])
+                return npts[k]
+            return step
+        fr = [C.byref(f) for f in fo]
+        move, tstep = tm.map.move_fast, tm.map.tiled_step_fast
+
+        def step(s):
+            k = pingpong(s, F)
+            move(posc[k])
+            tstep(xp[k], rp[k], npts[k], fr[k])
+            return npts[k]
+        return step
+    step = make_step(fobjs)
+    step_bal = make_step(fobjs_bal)
 
     sampler = ClockSampler(local).start() if rank == 0 else None
     s0 = 0
@@ -411,8 +434,10 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pts = 0
     e0.record(stream)
+    t_host = time.perf_counter()
     for s in range(K):
         pts += step(s0 + s)
+    host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / K
     tm.map.flush()        # the last step's fold (deferred by the step pipeline)
     e1.record(stream)
     torch.cuda.synchronize()
@@ -424,13 +449,13 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
     # ---- the same steps with a balanced rig (SURVEY's rig leaves the outer tiles of a 2 x 4 split without a sensor:
     # at 8 GPUs four ranks fold two sensors' points each and four fold almost none) ----
     for s in range(10):
-        k = pingpong(s, F); tm.add(xyzi_d[k], rgba_d[k], fobjs_bal[k])
+        step_bal(s)
     tm.map.sync(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     Kb = min(K, 300)
     bpts = 0
     e0.record(stream)
     for s in range(Kb):
-        k = pingpong(10 + s, F); tm.add(xyzi_d[k], rgba_d[k], fobjs_bal[k]); bpts += npts[k]
+        bpts += step_bal(10 + s)
     tm.map.flush()
     e1.record(stream)
     torch.cuda.synchronize()
@@ -500,7 +525,8 @@ def bench(args, gen_frames, pingpong, laser_frame, ClockSampler, load_peaks, alg
             "clocks": clocks, "gpu_launches": int(tot[1].item()),
             "tiled_parity": parity,
             "extra": {"rank0_last_step_stats": last_stats, "balanced_rig": balanced, "rank0_last_step_stats_balanced": bal_stats,
-                      "rig": "SURVEY 8d: sensors 50 m apart on a tiles_r x tiles_c rig centred on the map"},
+                      "rig": "SURVEY 8d: sensors 50 m apart on a tiles_r x tiles_c rig centred on the map",
+                      "host_enqueue_ms_per_step_rank0": host_enqueue_ms},
         }
     dist.barrier()
     dist.destroy_process_group()
