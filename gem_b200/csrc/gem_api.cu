@@ -531,8 +531,8 @@ int pipe_setup(gem_map *m)
     return GEM_OK;
 }
 
-// {fold(previous call) || bin(this call)} as a two-node graph, built once per bin kernel; per call only the node
-// parameters change.  One cudaGraphLaunch replaces two launches, two event records and two stream waits.
+// {long lists, other lists of the previous call || bin of this call} as a three-node graph, built once per bin kernel; per
+// call only the node parameters change.  One cudaGraphLaunch replaces three launches, two event records and two stream waits.
 int launch_frame_graph(gem_map *m, BinKernel bk, void **bin_args, int bin_grid, void **fold_args, int fold_grid, void **long_args, int long_grid)
 {
     FrameGraph &fg = m->graphs[(const void *)bk];

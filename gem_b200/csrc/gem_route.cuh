@@ -193,21 +193,23 @@ inline cudaError_t route_points(cudaStream_t st, const MapGeom &g, const FramePa
 //   k_route_peer   (source rank r)  1 thread/point: transform, owner tile, stable position inside the block's
 //                  sub-bucket, record stored straight into the owner's receive buffer over NVLink; every block also
 //                  stores its per-owner count; the last block to finish raises this rank's flag on every peer
-//   k_bin_peer     (owner rank)     1 block per (source rank, source block) sub-bucket of 256 slots: waits for all
-//                  peers' flags of this step, skips empty sub-buckets, bins the received records like k_bin does
+//   k_bin_peer     (owner rank)     one wave of blocks over the (source rank, source block) sub-buckets of 256 slots: waits
+//                  for all peers' flags of this step, skips empty sub-buckets, bins the received records like k_bin does
 //
 // Determinism: rank r's block b owns slots [(r * nblk + b) * 256, +256) of every owner's buffer, filled in source
 // order without a cross-block scan.  The slot index is monotone in (source rank, source point index), and it is the
 // slot index that the fold sorts a cell's records by -- so the tiled map equals the single-GPU map of the rank-by-rank
 // concatenated clouds bit for bit, although the buffer has holes.  The work list (marks) is dense and in no particular
 // order (the fold's result does not depend on which thread folds a cell): a sub-bucket takes its range with one atomic.
-// Steps are pipelined three deep: the graph of call j runs {route of step j || bin of step j-1 || folds of step j-2}, so
-// the flags a bin kernel waits for were raised one whole graph earlier (no rank waits for a peer unless that peer is a
-// full step behind) and route -> bin is not a dependent chain inside a step.
-// Receive buffers: PEER_BUFS = 5 by step.  Peer p's route of step k+5 rewrites this rank's buffer k % 5, which this rank's
-// fold of step k reads (intensities) in its graph k+2.  p's graph k+5 starts after p's graph k+4, whose bin of step k+3
-// waited for this rank's flag k+3, raised by this rank's route in ITS graph k+3, which started after its graph k+2 had
-// completed.  (Four buffers would not do: flag k+2 is raised inside the very graph k+2 that still folds step k.)
+// Step pipeline (gem_api.cu, gem_tiled_step).  Default, depth 2: the graph of call j runs {folds of step j-1 || route ->
+// bin of step j}.  Depth 3 (GEM_B200_TILED_DEPTH=3, measured slower, kept as a switch): {folds of step j-2 || bin of step
+// j-1 || route of step j}, all four kernels independent.
+// Receive buffers: PEER_BUFS = 5 by step, sized for depth 3.  There peer p's route of step k+5 rewrites this rank's buffer
+// k % 5, which this rank's fold of step k reads (intensities) in its graph k+2.  p's graph k+5 starts after p's graph k+4,
+// whose bin of step k+3 waited for this rank's flag k+3, raised by this rank's route in ITS graph k+3, which started after
+// its graph k+2 had completed.  (Four buffers would not do: flag k+2 is raised inside the very graph k+2 that still folds
+// step k.)  Depth 2 needs three: the fold of step k runs in graph k+1; p's route of step k+3 follows p's bin of step k+2,
+// which waited for this rank's flag k+2, raised in its graph k+2, i.e. after its graph k+1.
 // =========================================================================================
 constexpr int PEER_BUFS = 5;
 struct PeerBufs { // device addresses valid on THIS device (own memory or peer mappings), per rank

@@ -363,11 +363,12 @@ int gem_refuse_submaps(gem_map *m, void *new_points32_device, int *n_new, void *
  * buffer over NVLink (slot = (r * cap / 256 + source block) * 256 + position in the block: deterministic, source
  * order), raise rank r's flag on every peer; then, once every peer's flag of this step is up, bin and fold what
  * arrived.  The result equals the single-GPU map of the rank-by-rank concatenated clouds bit for bit.  Steps are
- * pipelined three deep: call j issues ONE graph {route of step j || bin of step j-1 || folds of step j-2}, so the
- * cloud of a call is consumed by that call's graph, and the map contains a step two calls later or after gem_flush /
- * gem_sync / any reading call (which issue the outstanding bin and folds).  Every rank must make the same sequence of
- * gem_tiled_step calls (a bin waits on the device for every peer's flag of its step).  GEM_B200_TILED_DEPTH=2 keeps
- * route -> bin of the same step in one graph (round-2 first version, for A/B). */
+ * pipelined like gem_add_points_stream: call j issues ONE graph {folds of step j-1 || route -> bin of step j}; the cloud
+ * of a call is consumed by that call's graph, and the map contains a step one call later or after gem_flush / gem_sync /
+ * any reading call (which issue what is outstanding).  Every rank must make the same sequence of gem_tiled_step calls (a
+ * bin waits on the device for every peer's flag of its step).  GEM_B200_TILED_DEPTH=3 selects a three-deep schedule
+ * {folds of step j-2 || bin of step j-1 || route of step j} (bit-identical, measured slower; it is what the five
+ * buffers are sized for). */
 typedef struct gem_tiled_peers {
     int tiles_r, tiles_c, my_rank, bucket_capacity;
     unsigned long long recv_records[64], recv_intensity[64], recv_counts[64], flags[64];
