@@ -49,6 +49,10 @@ struct BinCounters { // one counter per 128-byte line
     int nmarks;   int pad6[31];  // tiled maps: marks written by k_bin_peer (the fold's work list length)
 };
 
+static_assert(sizeof(BinCounters) == 7 * 128, "one counter per 128-byte line");
+static_assert(sizeof(BinCounters) / sizeof(int) <= 256, "zero_next_counters: one thread per word of a 256-thread block");
+static_assert(FOLD_LONG_FROM == CHUNK0 + 32 && CHUNK1_SLOTS == 33, "second chunk = header + ranks 8..39");
+
 // what point i was for its cell: nothing, or the point that drew rank 0 / 8 / 40.  The fold finds its work here.
 enum { MARK_NONE = 0, MARK_FIRST = 1, MARK_LARGE = 2, MARK_LONG = 3 };
 
@@ -149,6 +153,7 @@ struct RouteRec { // 20 bytes on the wire between tiles (gem_route.cuh)
     uint32_t rgb;
     float intensity;
 };
+static_assert(sizeof(RouteRec) == 20, "20 bytes on the wire");
 
 struct BinSource {
     // SRC_XYZI: float4 {x,y,z,intensity} + optional uchar4 rgba; SRC_PCL32: 2 x float4 per point (PointXYZRGBICT.hpp:26-48)

@@ -15,6 +15,8 @@ struct SubPoint { // PointXYZRGBICT.hpp:26-48, 32 bytes
     float covariance, intensity, travers;
 };
 
+static_assert(sizeof(SubPoint) == 32, "PointXYZRGBICT is 32 bytes");
+
 // pcl::transformPointCloud (ElevationMapping.cpp:805): x' = t00 x + t01 y + t02 z + t03, left to right in float (the
 // scalar code of PCL <= 1.9; PCL is an unpinned dependency of the reference).  T: row-major 4 x 4.
 struct Rigid { float t[12]; };
