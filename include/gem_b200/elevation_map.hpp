@@ -131,6 +131,34 @@ class ElevationMap {
     {
         check(gem_add_points(h_, xyzi_device, rgba_device, (int)n, &frame), "gem_add_points");
     }
+    // The same, frame-pipelined: the per-cell fold of this call is issued together with the NEXT call's binning (one CUDA
+    // graph per call); whatever reads the map next -- or flush() -- issues the last fold.  `xyzi_device` must stay valid
+    // until then (the fold reads the intensities from it).
+    void addStream(const void *xyzi_device, const void *rgba_device, size_t n, const gem_frame &frame)
+    {
+        check(gem_add_points_stream(h_, xyzi_device, rgba_device, (int)n, &frame), "gem_add_points_stream");
+    }
+    // several sensors' clouds in ONE launch (offsets[0] = 0 ... offsets[n_segments] = total points, one gem_frame each):
+    // equal to adding them one after the other
+    void addMulti(const void *xyzi_device, const void *rgba_device, int n_segments, const int *offsets, const gem_frame *frames)
+    {
+        check(gem_add_points_multi(h_, xyzi_device, rgba_device, n_segments, offsets, frames), "gem_add_points_multi");
+    }
+    // pinned host float4 / uchar4 buffers: the copy runs on a copy stream under the previous frame's kernels, no host
+    // synchronisation (three staging sets rotate)
+    void addHostAsync(const void *xyzi_pinned, const void *rgba_pinned, size_t n, const gem_frame &frame)
+    {
+        check(gem_add_points_host_async(h_, xyzi_pinned, rgba_pinned, (int)n, &frame), "gem_add_points_host_async");
+    }
+    void flush() { check(gem_flush(h_), "gem_flush"); }
+    // ElevationMapping::Callback's image branch (ElevationMapping.cpp:331-381): colours for a device cloud from a device
+    // BGR8 image; T_camera 3x4, T_lidar 4x4, row-major doubles as the node's yaml files hold them
+    void colourise(void *xyzi_device, size_t n, const double T_camera[12], const double T_lidar[16], const unsigned char *bgr_device,
+                   int width, int height, int row_stride_bytes, void *rgba_out_device)
+    {
+        check(gem_colourise_points(h_, xyzi_device, (int)n, T_camera, T_lidar, bgr_device, width, height, row_stride_bytes,
+                                   rgba_out_device), "gem_colourise_points");
+    }
     // RobotMotionMapUpdater::update -> Mapvar_update (RobotMotionMapUpdater.cpp:81)
     void update(float variance_increment) { check(gem_var_update(h_, variance_increment), "gem_var_update"); }
     // upstream ElevationMap::fuse: Map_feature + show's write-back into grid_map layers
@@ -142,6 +170,16 @@ class ElevationMap {
                          out.color_r.data(), out.color_g.data(), out.color_b.data(), out.intensity.data()};
         check(gem_export_layers(h_, ptr), "gem_export_layers");
     }
+    // fuse() in two halves: fuseBegin starts the write-back on a copy stream and returns, fuseEnd waits for it.  Work
+    // that does not change what was exported may be issued in between -- the node calls Raytracing right after show()
+    // (ElevationMapping.cpp:404-421): fuseBegin(out); clean(); fuseEnd();  `out` must be page-locked for the copy to
+    // overlap (gem_host_alloc) and must not be touched before fuseEnd.
+    void fuseBegin(float *layers_pinned[9])
+    {
+        check(gem_compute_features(h_), "gem_compute_features");
+        check(gem_export_layers_begin(h_, layers_pinned), "gem_export_layers_begin");
+    }
+    void fuseEnd() { check(gem_export_layers_end(h_), "gem_export_layers_end"); }
     // the rest of ElevationMap::show (ElevationMap.cpp:87,112-125), valid after fuse(): the bgr8 orthomosaic
     // (length x length x 3, cv::Mat CV_8UC3 layout) and the pcl::PointXYZRGB visual cloud (xyz + rgb per shown cell)
     void orthomosaic(std::vector<unsigned char> &bgr)
@@ -172,6 +210,22 @@ class ElevationMap {
         out.resize((size_t)n);
         if (n) check(gem_harvest_scrolled_out(h_, current, shift, out.data(), n, &n), "gem_harvest_scrolled_out");
         return n;
+    }
+    // Loop closure (ElevationMapping::updateGlobalMap, ElevationMapping.cpp:773-905), on device-resident submaps of
+    // PointXYZRGBICT records: re-pose a submap (:805), and one pass of the pairwise fuse loop (:847-883) -- both clouds
+    // come back reduced to one point per cell and compacted, *n_new / *n_old updated.  compat_precedence = true evaluates
+    // :862-863 exactly as C parses them.  The kd-tree loop around them stays with the caller.
+    void transformCloud(void *points32_device, size_t n, const float T_rowmajor[16])
+    {
+        check(gem_transform_cloud(h_, points32_device, (int)n, T_rowmajor), "gem_transform_cloud");
+    }
+    int refuseSubmaps(void *new_points32_device, int *n_new, void *old_points32_device, int *n_old, double resolution,
+                      bool compat_precedence = true)
+    {
+        int fused = 0;
+        check(gem_refuse_submaps(h_, new_points32_device, n_new, old_points32_device, n_old, resolution, compat_precedence ? 1 : 0, &fused),
+              "gem_refuse_submaps");
+        return fused;
     }
     // upstream visibilityCleanup / GEM Raytracing (gpu_process.cu:1304)
     void clean() { check(gem_raytracing(h_), "gem_raytracing"); }
