@@ -1,4 +1,5 @@
-// gem_add.cuh -- the add path of libgem_b200: Process_points + Fuse (gpu.cu:384-455, 477-537) in TWO kernels.
+// gem_add.cuh -- the add path of libgem_b200: Process_points + Fuse (gpu.cu:384-455, 477-537): one bin kernel, two fold
+// kernels that run side by side (the few hundred cells with more than 40 records have a kernel of their own).
 //
 //   k_bin   1 thread/point : float4 load, SE(3), filters, sensor variance, cell key, per-cell arrival rank via one
 //                            L2 atomic on the cell's own 32-byte record, 16-byte record {point index, h, var, rgb}
@@ -10,6 +11,9 @@
 //                            G_fuse's per-cell loop visits them), sequential Kalman fold with the 5-sigma gate,
 //                            lowest-scan update, one 16 B write-back per cell.  The cells are found through a
 //                            per-point mark array (point i drew rank 0 / 8 / 40 of cell c): no global lists
+//   k_fold_long  1 warp/cell with more than 40 records, drawn from the queue k_bin filled (one atomic per such cell):
+//                            the longest list of a frame is the latency of the fold, and it runs 2-4x faster on a
+//                            scheduler of its own than next to seven busy warps
 //
 // Round 1 had four kernels (transform+bin, per-cell allocation, scatter, fold) and five per-cell arrays; every
 // touched cell cost five random 32-byte sectors per call.  Here a cell IS one sector and the allocation and scatter
